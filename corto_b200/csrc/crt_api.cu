@@ -1,0 +1,736 @@
+// crt_api.cu — the C ABI of include/corto_b200.h: batch object (device-resident decode), single-decoder API with
+// host buffers, and the reference shims' own symbol names.  Host orchestration only; every byte of decode work
+// happens in crt_kernels.cu.  There is no CPU decode path in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/corto_b200.h"
+#include "crt_common.h"
+#include "crt_kernels.h"
+#include "crt_walk.h"
+
+using namespace crtb;
+
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char *what) {
+	g_err = std::string(what) + ": " + cudaGetErrorString(e);
+	return CRT_E_CUDA;
+}
+#define CU(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) return cuda_fail(e_, #x); } while(0)
+
+extern "C" const char *crt_last_error(void) { return g_err.c_str(); }
+
+extern "C" int crt_device_available(void) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if(e != cudaSuccess || n == 0) { g_err = std::string("no CUDA device: ") + cudaGetErrorString(e); cudaGetLastError(); return 0; }
+	return 1;
+}
+
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1)/a*a; }
+
+// ---------------------------------------------------------------------------------------------------------
+struct Binding { void *ptr; int format; int components; };
+
+struct Stage { const char *name; cudaEvent_t ev; };
+
+struct crt_batch {
+	std::vector<ParsedMesh> meshes;
+	std::vector<uint64_t> vert_base, face_base;
+	uint64_t total_bytes = 0;
+	std::map<std::string, Binding> binds;
+
+	// host images of the device tables
+	std::vector<MeshDesc> h_mesh;
+	std::vector<TunDesc> h_tun;
+	std::vector<uint32_t> h_groups;
+	std::vector<Tile> t_tun, t_bits, t_cloud, t_dequant, t_faces, t_verts, t_vscan;
+	std::vector<uint2> w_delta;
+	std::vector<uint32_t> clers_order;
+	bool any_border = false;
+
+	// device
+	int device = 0, sms = 148;
+	uint8_t *d_blobs = nullptr;        size_t blobs_bytes = 0;
+	uint8_t *d_tables = nullptr;       size_t tables_bytes = 0;     // MeshDesc | TunDesc | groups | tiles ... (one H2D)
+	std::vector<uint8_t> h_tables;
+	uint8_t *d_scratch = nullptr;      size_t scratch_bytes = 0;    // symbols, per-mesh work, dictionaries, CLERS slots
+	uint8_t *d_zero = nullptr;         size_t zero_bytes = 0;       // region cleared at every decode: tickets, states, status, csr counters
+	std::vector<uint8_t> h_pinned_stage;
+	// offsets inside d_tables
+	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_cloud = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
+	       o_t_vscan = 0, o_w_delta = 0, o_order = 0;
+	// offsets inside d_zero
+	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_states = 0, z_csr = 0;
+	size_t n_states = 0;
+	// scratch pieces
+	uint8_t *d_symbols = nullptr, *d_tunrec = nullptr; uint32_t *d_tun_used = nullptr;
+	ClersScratch clers{};
+	bool uploaded = false;
+	int launches = 0;
+	bool profiling = false;
+	std::vector<Stage> stages;
+	std::vector<int> h_status;
+};
+
+extern "C" crt_batch *crt_batch_create(int n, const unsigned char *const *blobs, const int *lens) {
+	if(n < 0 || (n > 0 && (!blobs || !lens))) { fail(CRT_E_ARG, "bad arguments"); return nullptr; }
+	crt_batch *b = new crt_batch();
+	b->meshes.resize(n);
+	b->vert_base.assign(n + 1, 0); b->face_base.assign(n + 1, 0);
+	for(int i = 0; i < n; i++) {
+		std::string err;
+		int rc = parse_header(blobs[i], lens[i], b->meshes[i], err);
+		if(rc == CRT_OK) rc = walk_directory(b->meshes[i], err);
+		if(rc != CRT_OK) { fail(rc, "blob " + std::to_string(i) + ": " + err); delete b; return nullptr; }
+		b->vert_base[i + 1] = b->vert_base[i] + b->meshes[i].nvert;
+		b->face_base[i + 1] = b->face_base[i] + b->meshes[i].nface;
+		b->total_bytes += (uint64_t)lens[i];
+	}
+	return b;
+}
+
+static void batch_free_device(crt_batch *b) {
+	if(b->d_blobs) cudaFree(b->d_blobs);
+	if(b->d_tables) cudaFree(b->d_tables);
+	if(b->d_scratch) cudaFree(b->d_scratch);
+	if(b->d_zero) cudaFree(b->d_zero);
+	b->d_blobs = b->d_tables = b->d_scratch = b->d_zero = nullptr;
+	for(auto &s: b->stages) cudaEventDestroy(s.ev);
+	b->stages.clear();
+	b->uploaded = false;
+}
+
+extern "C" void crt_batch_destroy(crt_batch *b) {
+	if(!b) return;
+	batch_free_device(b);
+	delete b;
+}
+
+extern "C" int crt_batch_count(const crt_batch *b) { return (int)b->meshes.size(); }
+extern "C" uint64_t crt_batch_total_verts(const crt_batch *b) { return b->vert_base.back(); }
+extern "C" uint64_t crt_batch_total_faces(const crt_batch *b) { return b->face_base.back(); }
+extern "C" uint64_t crt_batch_total_bytes(const crt_batch *b) { return b->total_bytes; }
+extern "C" const uint64_t *crt_batch_vert_base(const crt_batch *b) { return b->vert_base.data(); }
+extern "C" const uint64_t *crt_batch_face_base(const crt_batch *b) { return b->face_base.data(); }
+
+extern "C" int crt_batch_mesh_info(const crt_batch *b, int i, uint32_t *nvert, uint32_t *nface, uint32_t *attr_mask) {
+	if(i < 0 || i >= (int)b->meshes.size()) return fail(CRT_E_ARG, "mesh index out of range");
+	const ParsedMesh &m = b->meshes[i];
+	if(nvert) *nvert = m.nvert;
+	if(nface) *nface = m.nface;
+	if(attr_mask) {
+		uint32_t k = m.nface ? CRT_HAS_INDEX : 0;
+		for(auto &a: m.attrs) {
+			if(a.name == "position") k |= CRT_HAS_POSITION;
+			else if(a.name == "normal") k |= CRT_HAS_NORMAL;
+			else if(a.name == "color") k |= CRT_HAS_COLOR;
+			else if(a.name == "uv") k |= CRT_HAS_UV;
+			else k |= CRT_HAS_OTHER;
+		}
+		*attr_mask = k;
+	}
+	return CRT_OK;
+}
+
+extern "C" int crt_batch_bind(crt_batch *b, const char *name, void *device_ptr, int format, int components) {
+	if(!name) return fail(CRT_E_ARG, "null attribute name");
+	if(!device_ptr) { b->binds.erase(name); b->uploaded = b->uploaded && false; return CRT_OK; }
+	b->binds[name] = Binding{device_ptr, format, components};
+	return CRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Build every host table from the parsed directories + the current bindings.
+static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_bytes, std::vector<uint64_t> &work_off /*per mesh*/,
+                        uint64_t &zero_csr_bytes, std::vector<uint64_t> &csr_off, uint64_t &adj_bytes, std::vector<uint64_t> &adj_off) {
+	const int n = (int)b->meshes.size();
+	b->h_mesh.assign(n, MeshDesc{});
+	b->h_tun.clear(); b->h_groups.clear();
+	b->t_tun.clear(); b->t_bits.clear(); b->t_cloud.clear(); b->t_dequant.clear(); b->t_faces.clear(); b->t_verts.clear(); b->t_vscan.clear();
+	b->w_delta.clear(); b->clers_order.clear();
+	b->any_border = false;
+	symbols_bytes = 0; work_bytes = 0; zero_csr_bytes = 0; adj_bytes = 0;
+	work_off.assign(n, 0); csr_off.assign(n, 0); adj_off.assign(n, 0);
+	uint64_t blob_off = 0;
+
+	auto add_block = [&](const ParsedMesh &pm, const Block &blk, uint64_t mesh_blob_off) -> int {
+		TunDesc td{};
+		td.probs_off = mesh_blob_off + blk.probs_off;
+		td.data_off = mesh_blob_off + blk.data_off;
+		td.out_off = symbols_bytes;
+		td.nsym = blk.nsym; td.size = blk.size; td.csize = blk.csize; td.raw = blk.raw ? 1 : 0;
+		td.tile0 = (uint32_t)b->t_tun.size();
+		symbols_bytes += align_up((uint64_t)blk.size + 4, 16);
+		const int id = (int)b->h_tun.size();
+		if(blk.size) {
+			if(blk.raw || blk.nsym <= 1) {
+				uint32_t nt = (blk.size + TUN_TILE*4 - 1)/(TUN_TILE*4);
+				for(uint32_t t = 0; t < nt; t++) b->t_tun.push_back(Tile{(uint32_t)id, 0, t, 1});
+			} else {
+				uint32_t nt = (blk.csize + TUN_TILE - 1)/TUN_TILE;
+				for(uint32_t t = 0; t < nt; t++) b->t_tun.push_back(Tile{(uint32_t)id, 0, t, t == 0 ? 1u : 0u});
+			}
+		}
+		b->h_tun.push_back(td);
+		(void)pm;
+		return id;
+	};
+
+	for(int i = 0; i < n; i++) {
+		const ParsedMesh &pm = b->meshes[i];
+		MeshDesc &M = b->h_mesh[i];
+		M.blob_off = blob_off; M.blob_len = pm.len;
+		M.nvert = pm.nvert; M.nface = pm.nface; M.nattr = (uint32_t)pm.attrs.size();
+		M.ngroups = (uint32_t)pm.group_ends.size(); M.group0 = (uint32_t)b->h_groups.size();
+		uint32_t prev = 0, maxg = 0;
+		for(uint32_t e: pm.group_ends) {
+			b->h_groups.push_back(e);
+			uint32_t ee = std::min(e, pm.nface);
+			if(ee > prev) maxg = std::max(maxg, ee - prev);
+			prev = e;
+		}
+		M.max_group_faces = maxg;
+		M.clers_tun = -1; M.position_attr = pm.find("position"); M.normal_attr = -1;
+		M.max_front = pm.max_front;
+		uint64_t wb = 0;                       // per-mesh work bytes (16-aligned pieces)
+		auto take = [&](uint64_t bytes) { uint64_t o = wb; wb += align_up(bytes, 16); return o; };
+		uint64_t pred_o = 0, face_o = 0;
+		if(pm.nface) {
+			M.clers_tun = add_block(pm, pm.clers, blob_off);
+			M.nclers = pm.clers.size;
+			M.split_off = blob_off + pm.split_off; M.split_nwords = pm.split_nwords;
+			pred_o = take((uint64_t)pm.nvert*16);
+			b->clers_order.push_back((uint32_t)i);
+		}
+		// index binding
+		auto ib = b->binds.find("index");
+		bool index_bound = pm.nface && ib != b->binds.end();
+		if(index_bound) {
+			if(ib->second.format != CRT_UINT32 && ib->second.format != CRT_UINT16) return fail(CRT_E_FORMAT, "index must be CRT_UINT32 or CRT_UINT16");
+			M.index16 = ib->second.format == CRT_UINT16;
+			M.index_ptr = (uint64_t)ib->second.ptr + b->face_base[i]*3*(M.index16 ? 2 : 4);
+		} else if(pm.nface) face_o = take((uint64_t)pm.nface*12);
+
+		std::vector<uint64_t> attr_work(pm.attrs.size(), 0);
+		for(size_t a = 0; a < pm.attrs.size(); a++) {
+			const ParsedAttr &pa = pm.attrs[a];
+			const AttrStreams &st = pm.streams[a];
+			AttrDesc &A = M.attr[a];
+			A.codec = pa.codec; A.N = pa.N; A.ncomp = pa.codec == CODEC_NORMAL ? 2 : pa.N;
+			A.strategy = pa.strategy; A.q = pa.q;
+			A.out_format = -1; A.out_components = pa.N; A.prediction = st.prediction;
+			for(int k = 0; k < 4; k++) A.qc[k] = st.qc[k];
+			A.bits_off = blob_off + st.bits_off; A.bits_nwords = st.bits_nwords;
+			A.ntun = (int)st.blocks.size();
+			A.count = st.blocks.empty() ? 0 : st.blocks[0].size;
+			auto it = b->binds.find(pa.name);
+			const bool bound = it != b->binds.end();
+			if(bound) {
+				const Binding &bd = it->second;
+				uint64_t stride;
+				if(pa.codec == CODEC_NORMAL) {
+					if(bd.format != CRT_FLOAT && bd.format != CRT_INT16) return fail(CRT_E_FORMAT, "Format not supported for normal attribute (float, int16 only)");
+					stride = bd.format == CRT_FLOAT ? 12 : 6;
+				} else if(pa.codec == CODEC_COLOR) {
+					if(bd.format != CRT_UINT8) return fail(CRT_E_FORMAT, "Unsupported color output format.");
+					if(bd.components < 1 || bd.components > 4) return fail(CRT_E_ARG, "colour components must be 1..4");
+					A.out_components = bd.components;
+					stride = (uint64_t)bd.components;
+				} else {
+					if(bd.format != CRT_FLOAT && bd.format != CRT_INT32 && bd.format != CRT_UINT32) return fail(CRT_E_FORMAT, "generic attributes decode to CRT_FLOAT, CRT_INT32 or CRT_UINT32");
+					stride = (uint64_t)pa.N*4;
+				}
+				A.out_format = bd.format;
+				A.out_ptr = (uint64_t)bd.ptr + b->vert_base[i]*stride;
+			}
+			// entropy blocks are registered only for attributes somebody consumes (unbound ones are skipped)
+			for(int k = 0; k < A.ntun; k++) A.tun[k] = bound ? add_block(pm, st.blocks[k], blob_off) : -1;
+			if(!bound) continue;
+			if(pa.codec == CODEC_NORMAL) attr_work[a] = take((uint64_t)pm.nvert*8 + 16);
+			if(pa.codec == CODEC_COLOR) attr_work[a] = take((uint64_t)pm.nvert*pa.N + 16);
+			// bit-unpack tiles: chain = all component streams of the attribute
+			const bool correlated = pa.codec == CODEC_NORMAL || (pa.codec == CODEC_GENERIC && (pa.strategy & S_CORRELATED));
+			bool first = true;
+			for(int k = 0; k < A.ntun; k++) {
+				uint32_t nt = (st.blocks[k].size + BIT_TILE - 1)/BIT_TILE;
+				for(uint32_t t = 0; t < nt; t++) { b->t_bits.push_back(Tile{(uint32_t)i, (uint32_t)(a | ((correlated ? 0 : k) << 8)), t, first ? 1u : 0u}); first = false; }
+			}
+			// delta inverse
+			const bool normal_diff = pa.codec == CODEC_NORMAL && st.prediction == N_DIFF;
+			if(pa.codec != CODEC_NORMAL || normal_diff) {
+				if(pm.nface) b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a));
+				else {
+					uint32_t nt = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE;
+					for(int k = 0; k < A.ncomp; k++) for(uint32_t t = 0; t < nt; t++) b->t_cloud.push_back(Tile{(uint32_t)i, (uint32_t)(a | (k << 8)), t, t == 0 ? 1u : 0u});
+				}
+			}
+			// dequantise (normals: only DIFF goes through k_dequant; ESTIMATED/BORDER are finished by k_normal_estimate)
+			if(pa.codec != CODEC_NORMAL || normal_diff) {
+				uint32_t nt = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE;
+				for(uint32_t t = 0; t < nt; t++) b->t_dequant.push_back(Tile{(uint32_t)i, (uint32_t)a, t, 0});
+			}
+			if(pa.codec == CODEC_NORMAL && !normal_diff && pm.nface) {
+				if(st.prediction != N_ESTIMATED && st.prediction != N_BORDER) return fail(CRT_E_FORMAT, "unknown normal prediction in stream");
+				M.normal_attr = (int)a;
+				if(st.prediction == N_BORDER) b->any_border = true;
+			}
+		}
+		if(M.normal_attr >= 0) {
+			if(M.position_attr < 0) return fail(CRT_E_NOPOSITION, "No position attribute found. Use DIFF normal strategy instead.");   // normal_attribute.cpp:219-221
+			if(M.attr[M.position_attr].out_format != CRT_FLOAT || !M.attr[M.position_attr].out_ptr)
+				return fail(CRT_E_NOPOSITION, "ESTIMATED/BORDER normals need the position attribute bound as float (normal_attribute.cpp:230)");
+			csr_off[i] = zero_csr_bytes;
+			zero_csr_bytes += align_up(((uint64_t)pm.nvert*4 + 2)*4, 16);
+			adj_off[i] = adj_bytes;
+			adj_bytes += align_up((uint64_t)pm.nface*12, 16);
+			uint32_t nf = (pm.nface + SCAN_TILE - 1)/SCAN_TILE, nv = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE, ns = (pm.nvert + 1 + SCAN_TILE - 1)/SCAN_TILE;
+			for(uint32_t t = 0; t < nf; t++) b->t_faces.push_back(Tile{(uint32_t)i, 0, t, 0});
+			for(uint32_t t = 0; t < nv; t++) b->t_verts.push_back(Tile{(uint32_t)i, 0, t, 0});
+			for(uint32_t t = 0; t < ns; t++) b->t_vscan.push_back(Tile{(uint32_t)i, 0, t, t == 0 ? 1u : 0u});
+		}
+		// stash per-mesh work offsets (resolved to pointers once the arena address is known)
+		M.pred_ptr = pred_o; M.face_ptr = face_o;
+		for(size_t a = 0; a < pm.attrs.size(); a++) M.attr[a].work_ptr = attr_work[a];
+		work_off[i] = work_bytes;
+		work_bytes += align_up(wb, 256);
+		blob_off += align_up(pm.len, 16);
+	}
+	// biggest meshes first: the serial automaton is the long pole (LPT order)
+	std::stable_sort(b->clers_order.begin(), b->clers_order.end(), [&](uint32_t x, uint32_t y) { return b->meshes[x].nface > b->meshes[y].nface; });
+	return CRT_OK;
+}
+
+template <class T> static size_t put(std::vector<uint8_t> &img, const std::vector<T> &v) {
+	size_t o = align_up(img.size(), 256);
+	img.resize(o + v.size()*sizeof(T) + 16);
+	if(!v.empty()) memcpy(img.data() + o, v.data(), v.size()*sizeof(T));
+	return o;
+}
+
+static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
+	CU(cudaGetDevice(&b->device));
+	CU(cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, b->device));
+	uint64_t symbols_bytes, work_bytes, csr_bytes, adj_bytes;
+	std::vector<uint64_t> work_off, csr_off, adj_off;
+	int rc = build_tables(b, symbols_bytes, work_bytes, work_off, csr_bytes, csr_off, adj_bytes, adj_off);
+	if(rc) return rc;
+	const int n = (int)b->meshes.size();
+
+	// ---- blob arena ----
+	uint64_t blobs_bytes = 16;
+	for(auto &m: b->meshes) blobs_bytes += align_up(m.len, 16);
+	if(copy_blobs || !b->d_blobs || b->blobs_bytes < blobs_bytes) {
+		if(b->d_blobs) { cudaFree(b->d_blobs); b->d_blobs = nullptr; }
+		CU(cudaMalloc(&b->d_blobs, blobs_bytes));
+		b->blobs_bytes = blobs_bytes;
+		for(int i = 0; i < n; i++)
+			CU(cudaMemcpyAsync(b->d_blobs + b->h_mesh[i].blob_off, b->meshes[i].blob, b->meshes[i].len, cudaMemcpyHostToDevice, stream));
+	}
+
+	// ---- scratch arena: symbols | per-mesh work | adj | dictionaries | CLERS slots ----
+	const uint64_t ntun = b->h_tun.size();
+	uint32_t cap = 16, nmesh_faces = (uint32_t)b->clers_order.size();
+	for(auto &M: b->h_mesh) if(M.nface) cap = std::max(cap, 3u*M.max_group_faces + 16u);
+	uint32_t slots = std::min<uint32_t>(nmesh_faces, (uint32_t)b->sms*4u);
+	const uint64_t per_slot = (uint64_t)cap*(sizeof(EdgeA) + sizeof(EdgeB) + 8);
+	while(slots > 1 && per_slot*slots > (48ull << 30)) slots /= 2;
+	uint64_t o_sym = 0, o_work = align_up(o_sym + symbols_bytes + 64, 256), o_adj = align_up(o_work + work_bytes, 256),
+	         o_rec = align_up(o_adj + adj_bytes, 256), o_used = align_up(o_rec + ntun*TUN_REC_BYTES, 256),
+	         o_clers = align_up(o_used + ntun*4 + 16, 256), total = o_clers + per_slot*slots + 256;
+	if(!b->d_scratch || b->scratch_bytes < total) {
+		if(b->d_scratch) { cudaFree(b->d_scratch); b->d_scratch = nullptr; }
+		CU(cudaMalloc(&b->d_scratch, total));
+		b->scratch_bytes = total;
+	}
+	b->d_symbols = b->d_scratch + o_sym;
+	b->d_tunrec = b->d_scratch + o_rec;
+	b->d_tun_used = (uint32_t *)(b->d_scratch + o_used);
+	b->clers.cap = cap; b->clers.slots = slots;
+	uint8_t *cs = b->d_scratch + o_clers;
+	b->clers.ea = (EdgeA *)cs; cs += (uint64_t)cap*slots*sizeof(EdgeA);
+	b->clers.eb = (EdgeB *)cs; cs += (uint64_t)cap*slots*sizeof(EdgeB);
+	b->clers.order = (uint32_t *)cs; cs += (uint64_t)cap*slots*4;
+	b->clers.delayed = (uint32_t *)cs;
+
+	// ---- zeroed control region: tickets | status | vertex_count | look-back states | csr counters ----
+	b->n_states = b->t_tun.size() + b->t_bits.size() + b->t_cloud.size() + 2*b->t_vscan.size();
+	b->z_ticket = 0;
+	b->z_status = 256;
+	b->z_vcount = align_up(b->z_status + (uint64_t)n*4, 256);
+	b->z_states = align_up(b->z_vcount + (uint64_t)n*4, 256);
+	b->z_csr = align_up(b->z_states + b->n_states*8, 256);
+	uint64_t zero_total = b->z_csr + csr_bytes + 256;
+	if(!b->d_zero || b->zero_bytes < zero_total) {
+		if(b->d_zero) { cudaFree(b->d_zero); b->d_zero = nullptr; }
+		CU(cudaMalloc(&b->d_zero, zero_total));
+	}
+	b->zero_bytes = zero_total;
+
+	// ---- resolve scratch pointers inside the descriptors ----
+	for(int i = 0; i < n; i++) {
+		MeshDesc &M = b->h_mesh[i];
+		uint8_t *w = b->d_scratch + o_work + work_off[i];
+		if(M.nface) {
+			M.pred_ptr = (uint64_t)(w + M.pred_ptr);
+			M.face_ptr = M.index_ptr ? M.index_ptr : (uint64_t)(w + M.face_ptr);
+			if(!M.index_ptr) M.index16 = 0;
+		} else { M.pred_ptr = 0; M.face_ptr = 0; }
+		for(uint32_t a = 0; a < M.nattr; a++) {
+			AttrDesc &A = M.attr[a];
+			if(A.out_format >= 0 && (A.codec == CODEC_NORMAL || A.codec == CODEC_COLOR)) A.work_ptr = (uint64_t)(w + A.work_ptr);
+			else A.work_ptr = 0;
+		}
+		if(M.normal_attr >= 0) {
+			M.csr_ptr = (uint64_t)(b->d_zero + b->z_csr + csr_off[i]);
+			M.adj_ptr = (uint64_t)(b->d_scratch + o_adj + adj_off[i]);
+		}
+	}
+
+	// ---- one table image, one H2D ----
+	std::vector<uint8_t> &img = b->h_tables;
+	img.clear();
+	b->o_mesh = put(img, b->h_mesh);
+	b->o_tun = put(img, b->h_tun);
+	b->o_groups = put(img, b->h_groups);
+	b->o_t_tun = put(img, b->t_tun);
+	b->o_t_bits = put(img, b->t_bits);
+	b->o_t_cloud = put(img, b->t_cloud);
+	b->o_t_dequant = put(img, b->t_dequant);
+	b->o_t_faces = put(img, b->t_faces);
+	b->o_t_verts = put(img, b->t_verts);
+	b->o_t_vscan = put(img, b->t_vscan);
+	b->o_w_delta = put(img, b->w_delta);
+	b->o_order = put(img, b->clers_order);
+	if(!b->d_tables || b->tables_bytes < img.size()) {
+		if(b->d_tables) { cudaFree(b->d_tables); b->d_tables = nullptr; }
+		CU(cudaMalloc(&b->d_tables, img.size() + 256));
+		b->tables_bytes = img.size() + 256;
+	}
+	CU(cudaMemcpyAsync(b->d_tables, img.data(), img.size(), cudaMemcpyHostToDevice, stream));
+	// the table image is pageable host memory owned by the batch; wait so it may be rebuilt safely
+	CU(cudaStreamSynchronize(stream));
+	b->uploaded = true;
+	return CRT_OK;
+}
+
+extern "C" int crt_batch_upload(crt_batch *b, void *stream) {
+	if(!crt_device_available()) return CRT_E_CUDA;
+	return batch_prepare(b, (cudaStream_t)stream, true);
+}
+
+extern "C" int crt_batch_rewalk(crt_batch *b, void *stream) {
+	if(!b->uploaded) return fail(CRT_E_ARG, "crt_batch_rewalk before crt_batch_upload");
+	for(size_t i = 0; i < b->meshes.size(); i++) {
+		std::string err;
+		int rc = walk_directory(b->meshes[i], err);
+		if(rc) return fail(rc, "blob " + std::to_string(i) + ": " + err);
+	}
+	return batch_prepare(b, (cudaStream_t)stream, false);
+}
+
+extern "C" int crt_batch_set_profiling(crt_batch *b, int on) { b->profiling = on != 0; return CRT_OK; }
+
+static int mark(crt_batch *b, const char *name, size_t &k, cudaStream_t s) {
+	if(!b->profiling) return CRT_OK;
+	if(k >= b->stages.size()) { Stage st{name, nullptr}; CU(cudaEventCreate(&st.ev)); b->stages.push_back(st); }
+	b->stages[k].name = name;
+	CU(cudaEventRecord(b->stages[k].ev, s));
+	k++;
+	return CRT_OK;
+}
+
+extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
+	if(!b->uploaded) return fail(CRT_E_ARG, "crt_batch_decode before crt_batch_upload");
+	cudaStream_t s = (cudaStream_t)stream_;
+	DevBatch B{};
+	B.blobs = b->d_blobs; B.symbols = b->d_symbols;
+	B.mesh = (const MeshDesc *)(b->d_tables + b->o_mesh);
+	B.tun = (const TunDesc *)(b->d_tables + b->o_tun);
+	B.tunrec = b->d_tunrec; B.tun_used = b->d_tun_used;
+	B.group_ends = (const uint32_t *)(b->d_tables + b->o_groups);
+	B.status = (int32_t *)(b->d_zero + b->z_status);
+	B.vertex_count = (uint32_t *)(b->d_zero + b->z_vcount);
+	uint32_t *tickets = (uint32_t *)(b->d_zero + b->z_ticket);
+	uint64_t *states = (uint64_t *)(b->d_zero + b->z_states);
+	const Tile *t_tun = (const Tile *)(b->d_tables + b->o_t_tun), *t_bits = (const Tile *)(b->d_tables + b->o_t_bits),
+	           *t_cloud = (const Tile *)(b->d_tables + b->o_t_cloud), *t_dequant = (const Tile *)(b->d_tables + b->o_t_dequant),
+	           *t_faces = (const Tile *)(b->d_tables + b->o_t_faces), *t_verts = (const Tile *)(b->d_tables + b->o_t_verts),
+	           *t_vscan = (const Tile *)(b->d_tables + b->o_t_vscan);
+	int launches = 0;
+	size_t k = 0;
+	int rc;
+#define RUN(call, cond) do { if(cond) { int e_ = (call); if(e_) return cuda_fail((cudaError_t)e_, #call); launches++; } } while(0)
+	if((rc = mark(b, "begin", k, s))) return rc;
+	CU(cudaMemsetAsync(b->d_zero, 0, b->zero_bytes, s));
+	RUN(launch_tun_tables(B, (int)b->h_tun.size(), s), !b->h_tun.empty());
+	if((rc = mark(b, "tun_tables", k, s))) return rc;
+	uint64_t *st = states;
+	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
+	st += b->t_tun.size();
+	if((rc = mark(b, "tun_decode", k, s))) return rc;
+	RUN(launch_bit_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st, tickets + 1, b->sms, s), !b->t_bits.empty());
+	st += b->t_bits.size();
+	if((rc = mark(b, "bit_unpack", k, s))) return rc;
+	RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, s), !b->clers_order.empty());
+	if((rc = mark(b, "clers", k, s))) return rc;
+	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
+	RUN(launch_delta_cloud(B, t_cloud, (uint32_t)b->t_cloud.size(), st, tickets + 3, b->sms, s), !b->t_cloud.empty());
+	st += b->t_cloud.size();
+	if((rc = mark(b, "delta", k, s))) return rc;
+	if(!b->t_faces.empty()) {
+		RUN(launch_csr_count(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
+		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, 0, b->sms, s), true);
+		st += b->t_vscan.size();
+		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 5, 1, b->sms, s), b->any_border);
+		RUN(launch_csr_fill(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
+		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
+	}
+	if((rc = mark(b, "normals", k, s))) return rc;
+	RUN(launch_dequant(B, t_dequant, (uint32_t)b->t_dequant.size(), s), !b->t_dequant.empty());
+	if((rc = mark(b, "dequant", k, s))) return rc;
+#undef RUN
+	b->launches = launches;
+	return CRT_OK;
+}
+
+extern "C" int crt_batch_launches(const crt_batch *b) { return b->launches; }
+
+extern "C" int crt_batch_stage_times(crt_batch *b, const char **names, float *ms, int cap) {
+	int n = 0;
+	for(size_t i = 1; i < b->stages.size() && n < cap; i++) {
+		float t = 0;
+		if(cudaEventElapsedTime(&t, b->stages[i - 1].ev, b->stages[i].ev) != cudaSuccess) { cudaGetLastError(); t = -1; }
+		names[n] = b->stages[i].name; ms[n] = t; n++;
+	}
+	return n;
+}
+
+extern "C" int crt_batch_status(crt_batch *b, int *per_mesh) {
+	const size_t n = b->meshes.size();
+	b->h_status.assign(n, 0);
+	if(n) CU(cudaMemcpy(b->h_status.data(), b->d_zero + b->z_status, n*4, cudaMemcpyDeviceToHost));
+	int first = CRT_OK;
+	for(size_t i = 0; i < n; i++) {
+		if(per_mesh) per_mesh[i] = b->h_status[i];
+		if(first == CRT_OK && b->h_status[i]) { first = b->h_status[i]; fail(first, "mesh " + std::to_string(i) + ": Decoding topology failed"); }
+	}
+	return first;
+}
+
+extern "C" int crt_batch_debug_clers(crt_batch *b, int i, unsigned char *out, uint32_t cap, uint32_t *nout) {
+	if(!b->uploaded || i < 0 || i >= (int)b->meshes.size()) return fail(CRT_E_ARG, "bad mesh index");
+	const MeshDesc &M = b->h_mesh[i];
+	if(M.clers_tun < 0) { *nout = 0; return CRT_OK; }
+	const TunDesc &td = b->h_tun[M.clers_tun];
+	*nout = td.size;
+	CU(cudaMemcpy(out, b->d_symbols + td.out_off, std::min(cap, td.size), cudaMemcpyDeviceToHost));
+	return CRT_OK;
+}
+
+extern "C" int crt_batch_debug_prediction(crt_batch *b, int i, uint32_t *out) {
+	if(!b->uploaded || i < 0 || i >= (int)b->meshes.size()) return fail(CRT_E_ARG, "bad mesh index");
+	const MeshDesc &M = b->h_mesh[i];
+	if(!M.nface) return CRT_OK;
+	std::vector<uint32_t> tmp((size_t)M.nvert*4);
+	CU(cudaMemcpy(tmp.data(), (const void *)M.pred_ptr, tmp.size()*4, cudaMemcpyDeviceToHost));
+	for(uint32_t v = 0; v < M.nvert; v++) { out[v*3] = tmp[v*4]; out[v*3 + 1] = tmp[v*4 + 1]; out[v*3 + 2] = tmp[v*4 + 2]; }
+	return CRT_OK;
+}
+
+extern "C" int crt_shard_lpt(int n, const uint32_t *nvert, const uint32_t *nface, const uint32_t *nattr, int world, int *rank_of) {
+	if(n < 0 || world < 1 || !rank_of) return fail(CRT_E_ARG, "bad arguments");
+	std::vector<int> order(n);
+	std::vector<double> cost(n);
+	for(int i = 0; i < n; i++) { order[i] = i; cost[i] = 4.0*(nface ? nface[i] : 0) + 1.0*(double)nvert[i]*(nattr ? nattr[i] : 1); }
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+	std::vector<double> load(world, 0.0);
+	for(int i: order) {
+		int best = 0;
+		for(int r = 1; r < world; r++) if(load[r] < load[best]) best = r;
+		rank_of[i] = best; load[best] += cost[i];
+	}
+	return CRT_OK;
+}
+
+// =========================================================================================================
+// single decoder with host buffers
+// =========================================================================================================
+struct HostBind { void *ptr; int format; int components; };
+
+struct crt_decoder {
+	ParsedMesh pm;
+	std::map<std::string, HostBind> binds;
+	void *index = nullptr; int index16 = 0;
+	std::vector<uint32_t> group_ends; std::vector<Props> group_props;
+	bool groups_known = false;
+	int normal_prediction = 0;
+	int qc[4] = {4, 4, 4, 8};
+};
+
+static void ensure_groups(crt_decoder *d) {
+	// the reference fills index.groups inside decode() (decoder.cpp:165); the shims read them after decode().
+	// Here the group table is parsed on first use so ngroups()/groups() also work before decode().
+	if(d->groups_known) return;
+	std::string err;
+	if(walk_directory(d->pm, err) == CRT_OK) { d->group_ends = d->pm.group_ends; d->group_props = d->pm.group_props; }
+	d->groups_known = true;
+}
+
+extern "C" crt_decoder *crt_new_decoder(int len, const unsigned char *buffer) {
+	crt_decoder *d = new crt_decoder();
+	std::string err;
+	int rc = parse_header(buffer, len, d->pm, err);
+	if(rc) { fail(rc, err); delete d; return nullptr; }
+	return d;
+}
+extern "C" void crt_delete_decoder(crt_decoder *d) { delete d; }
+extern "C" uint32_t crt_nvert(const crt_decoder *d) { return d->pm.nvert; }
+extern "C" uint32_t crt_nface(const crt_decoder *d) { return d->pm.nface; }
+extern "C" int crt_ngroups(const crt_decoder *d) { ensure_groups((crt_decoder *)d); return (int)d->group_ends.size(); }
+extern "C" void crt_groups(const crt_decoder *d, int *ends) { ensure_groups((crt_decoder *)d); for(size_t i = 0; i < d->group_ends.size(); i++) ends[i] = (int)d->group_ends[i]; }
+extern "C" int crt_group_nprops(const crt_decoder *d, int g) { ensure_groups((crt_decoder *)d); return (g < 0 || g >= (int)d->group_props.size()) ? 0 : (int)d->group_props[g].size(); }
+extern "C" const char *crt_group_prop(const crt_decoder *d, int g, int i, const char **value) {
+	ensure_groups((crt_decoder *)d);
+	if(g < 0 || g >= (int)d->group_props.size() || i < 0 || i >= (int)d->group_props[g].size()) return nullptr;
+	if(value) *value = d->group_props[g][i].second.c_str();
+	return d->group_props[g][i].first.c_str();
+}
+extern "C" int crt_nexif(const crt_decoder *d) { return (int)d->pm.exif.size(); }
+extern "C" const char *crt_exif(const crt_decoder *d, int i, const char **value) {
+	if(i < 0 || i >= (int)d->pm.exif.size()) return nullptr;
+	if(value) *value = d->pm.exif[i].second.c_str();
+	return d->pm.exif[i].first.c_str();
+}
+extern "C" int crt_has_attr(const crt_decoder *d, const char *name) { return d->pm.find(name) >= 0; }
+extern "C" int crt_nattr(const crt_decoder *d) { return (int)d->pm.attrs.size(); }
+extern "C" const char *crt_attr_info(const crt_decoder *d, int i, int *codec, float *q, int *components, int *format, int *strategy) {
+	if(i < 0 || i >= (int)d->pm.attrs.size()) return nullptr;
+	const ParsedAttr &a = d->pm.attrs[i];
+	if(codec) *codec = a.codec; if(q) *q = a.q; if(components) *components = a.N; if(format) *format = a.format; if(strategy) *strategy = a.strategy;
+	return a.name.c_str();
+}
+
+extern "C" int crt_set_attribute(crt_decoder *d, const char *name, char *buffer, int format) {   // decoder.cpp:96-102
+	if(d->pm.find(name) < 0) return 0;
+	int comps = d->pm.attrs[d->pm.find(name)].N;
+	auto it = d->binds.find(name);
+	if(it != d->binds.end()) comps = it->second.components;
+	d->binds[name] = HostBind{buffer, format, comps};
+	return 1;
+}
+extern "C" int crt_set_positions(crt_decoder *d, float *b) { return crt_set_attribute(d, "position", (char *)b, CRT_FLOAT); }
+extern "C" int crt_set_normals32(crt_decoder *d, float *b) { return crt_set_attribute(d, "normal", (char *)b, CRT_FLOAT); }
+extern "C" int crt_set_normals16(crt_decoder *d, int16_t *b) { return crt_set_attribute(d, "normal", (char *)b, CRT_INT16); }
+extern "C" int crt_set_uvs(crt_decoder *d, float *b) { return crt_set_attribute(d, "uv", (char *)b, CRT_FLOAT); }
+extern "C" int crt_set_colors(crt_decoder *d, unsigned char *b, int components) {               // decoder.cpp:116-123
+	if(d->pm.find("color") < 0) return 0;
+	d->binds["color"] = HostBind{b, CRT_UINT8, components};
+	return 1;
+}
+extern "C" void crt_set_index32(crt_decoder *d, uint32_t *b) { d->index = b; d->index16 = 0; }
+extern "C" void crt_set_index16(crt_decoder *d, uint16_t *b) { d->index = b; d->index16 = 1; }
+extern "C" int crt_normal_prediction(const crt_decoder *d) { return d->normal_prediction; }
+extern "C" void crt_color_q(const crt_decoder *d, int qc[4]) { for(int k = 0; k < 4; k++) qc[k] = d->qc[k]; }
+
+extern "C" int crt_decode(crt_decoder *d) {
+	if(!crt_device_available()) return CRT_E_CUDA;
+	const unsigned char *blob = d->pm.blob;
+	int len = (int)d->pm.len;
+	crt_batch *b = crt_batch_create(1, &blob, &len);
+	if(!b) return CRT_E_TRUNCATED;
+	d->group_ends = b->meshes[0].group_ends; d->group_props = b->meshes[0].group_props; d->groups_known = true;
+	const ParsedMesh &pm = b->meshes[0];
+	struct Out { void *dev; void *host; size_t bytes; };
+	std::vector<Out> outs;
+	int rc = CRT_OK;
+	auto cleanup = [&]() { for(auto &o: outs) cudaFree(o.dev); crt_batch_destroy(b); };
+	for(size_t a = 0; a < pm.attrs.size() && rc == CRT_OK; a++) {
+		const ParsedAttr &pa = pm.attrs[a];
+		if(pa.codec == CODEC_NORMAL) d->normal_prediction = pm.streams[a].prediction;
+		if(pa.codec == CODEC_COLOR) for(int k = 0; k < 4; k++) d->qc[k] = pm.streams[a].qc[k];
+		auto it = d->binds.find(pa.name);
+		if(it == d->binds.end() || !it->second.ptr) continue;
+		const HostBind &hb = it->second;
+		size_t stride;
+		if(pa.codec == CODEC_NORMAL) stride = hb.format == CRT_INT16 ? 6 : 12;
+		else if(pa.codec == CODEC_COLOR) stride = (size_t)hb.components;
+		else stride = (size_t)pa.N*4;
+		Out o{nullptr, hb.ptr, stride*pm.nvert};
+		cudaError_t e = cudaMalloc(&o.dev, o.bytes + 16);
+		if(e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(output)"); break; }
+		outs.push_back(o);
+		// the caller's buffer content is preserved where the reference leaves elements untouched
+		if(pa.codec == CODEC_NORMAL && hb.format == CRT_INT16) cudaMemcpy(o.dev, o.host, o.bytes, cudaMemcpyHostToDevice);
+		rc = crt_batch_bind(b, pa.name.c_str(), o.dev, hb.format, hb.components);
+	}
+	if(rc == CRT_OK && pm.nface && d->index) {
+		Out o{nullptr, d->index, (size_t)pm.nface*3*(d->index16 ? 2 : 4)};
+		cudaError_t e = cudaMalloc(&o.dev, o.bytes + 16);
+		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(index)");
+		else { outs.push_back(o); rc = crt_batch_bind(b, "index", o.dev, d->index16 ? CRT_UINT16 : CRT_UINT32, 0); }
+	}
+	if(rc == CRT_OK) rc = crt_batch_upload(b, nullptr);
+	if(rc == CRT_OK) rc = crt_batch_decode(b, nullptr);
+	if(rc == CRT_OK) { cudaError_t e = cudaStreamSynchronize(nullptr); if(e != cudaSuccess) rc = cuda_fail(e, "decode kernels"); }
+	if(rc == CRT_OK) rc = crt_batch_status(b, nullptr);
+	if(rc == CRT_OK) for(auto &o: outs) {
+		cudaError_t e = cudaMemcpy(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost);
+		if(e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpy(D2H)"); break; }
+	}
+	std::string keep = g_err;
+	cleanup();
+	if(rc != CRT_OK) g_err = keep;
+	return rc;
+}
+
+// =========================================================================================================
+// the reference shims' own names (emcorto.cpp:14-89, corto_codec.h:41-43)
+// =========================================================================================================
+extern "C" crt_decoder *newDecoder(int n, const unsigned char *buffer) { return crt_new_decoder(n, buffer); }
+extern "C" void deleteDecoder(crt_decoder *d) { crt_delete_decoder(d); }
+extern "C" int ngroups(crt_decoder *d) { return crt_ngroups(d); }
+extern "C" void groups(crt_decoder *d, int *ends) { crt_groups(d, ends); }
+extern "C" int nvert(crt_decoder *d) { return (int)crt_nvert(d); }
+extern "C" int nface(crt_decoder *d) { return (int)crt_nface(d); }
+extern "C" int hasAttr(crt_decoder *d, const char *attr) { return crt_has_attr(d, attr); }
+extern "C" int hasNormal(crt_decoder *d) { return crt_has_attr(d, "normal"); }
+extern "C" int hasColor(crt_decoder *d) { return crt_has_attr(d, "color"); }
+extern "C" int hasUv(crt_decoder *d) { return crt_has_attr(d, "uv"); }
+extern "C" void setPositions(crt_decoder *d, float *b) { crt_set_positions(d, b); }
+extern "C" void setNormals32(crt_decoder *d, float *b) { crt_set_normals32(d, b); }
+extern "C" void setNormals16(crt_decoder *d, int16_t *b) { crt_set_normals16(d, b); }
+extern "C" void setColors(crt_decoder *d, unsigned char *b, int components) { crt_set_colors(d, b, components); }
+extern "C" void setUvs(crt_decoder *d, float *b) { crt_set_uvs(d, b); }
+extern "C" void setIndex16(crt_decoder *d, uint16_t *b) { crt_set_index16(d, b); }
+extern "C" void setIndex32(crt_decoder *d, uint32_t *b) { crt_set_index32(d, b); }
+extern "C" void decode(crt_decoder *d) { crt_decode(d); }
+
+extern "C" crt_decoder *CreateDecoder(int length, unsigned char *data, crt_Vector2 *info) {
+	crt_decoder *d = crt_new_decoder(length, data);
+	if(d && info) { info->x = (float)d->pm.nface; info->y = (float)d->pm.nvert; }   // corto_codec.cpp:11-14
+	return d;
+}
+extern "C" void DestroyDecoder(crt_decoder *d) { crt_delete_decoder(d); }
+extern "C" int DecodeMesh(crt_decoder *d, crt_Vector3 *vertices, int *indices, crt_Vector3 *normals, crt_Color *colors, crt_Vector2 *texcoord) {
+	if(d->pm.nface == 0) return -1;                                                  // corto_codec.cpp:27-30
+	crt_set_index32(d, (uint32_t *)indices);
+	if(d->pm.nvert > 0) crt_set_positions(d, (float *)vertices);
+	if(crt_has_attr(d, "normal")) crt_set_normals32(d, (float *)normals);
+	std::vector<unsigned char> rgba;
+	if(crt_has_attr(d, "color") && colors) { rgba.resize((size_t)d->pm.nvert*4); crt_set_colors(d, rgba.data(), 4); }
+	if(crt_has_attr(d, "uv")) crt_set_uvs(d, (float *)texcoord);
+	if(crt_decode(d) != CRT_OK) return -1;
+	for(size_t i = 0; i < rgba.size()/4; i++) {
+		colors[i].r = rgba[i*4]/255.0f; colors[i].g = rgba[i*4 + 1]/255.0f; colors[i].b = rgba[i*4 + 2]/255.0f; colors[i].a = rgba[i*4 + 3]/255.0f;
+	}
+	return (int)d->pm.nface;
+}

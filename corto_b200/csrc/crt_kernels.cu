@@ -1,0 +1,673 @@
+// crt_kernels.cu — hand-written sm_100a kernels of the corto decode path (no tensor cores: there is no dense
+// contraction anywhere in this path, it is byte / bit / index work bound by HBM and by one serial automaton).
+//
+// Kernel      replaces (reference file:line)                                      parallel structure
+// k_tun_tables   Tunstall::createDecodingTables2   src/tunstall.cpp:125-256       one warp per entropy block
+// k_tun_decode   Tunstall::decompress              src/tunstall.cpp:430-452       tiles of compressed bytes; the
+//                + InStream::decompress NONE path  src/cstream.cpp:68-73          dictionary staged in smem by TMA
+//                                                                                 (cp.async.bulk + mbarrier); output
+//                                                                                 offset = decoupled look-back scan
+// k_bit_unpack   decodeArray / decodeValues        include/corto/cstream.h:294-360 tiles of logs; bit offset = scan
+// k_clers        Decoder::decodeFaces              src/decoder.cpp:204-358        serial automaton, one warp / mesh
+// k_delta_mesh   GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp / (mesh, attr), lane / comp
+//                NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
+// k_delta_cloud  ... (point cloud)                 vertex_attribute.h:177-181, normal_attribute.cpp:202-207
+// k_csr_count / k_scan_u32 / k_csr_fill / k_normal_estimate
+//                markBoundary, estimateNormals, computeNormals   normal_attribute.cpp:24-59, 281-325
+// k_dequant      GenericAttr::dequantize, NormalAttr::dequantize, ColorAttr::dequantize
+//                vertex_attribute.h:184-230, normal_attribute.cpp:257-279, color_attribute.cpp:76-95
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "crt_device.cuh"
+#include "crt_kernels.h"
+
+namespace crtb {
+
+// =========================================================================================================
+// small device utilities
+// =========================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- decoupled look-back over a chain of tiles ------------------------------------------------------------
+// state word: bits 63..62 = 0 empty | 1 aggregate | 2 inclusive prefix; bits 61..0 = value.  One 64-bit word
+// carries flag and value together, so a relaxed volatile load/store pair is enough.  Tiles are taken in ticket
+// order, hence every predecessor of a running tile is running or done: the spin cannot deadlock.
+constexpr uint64_t LB_AGG = 1ull << 62, LB_PFX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t lb_load(const uint64_t *p) {
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void lb_store(uint64_t *p, uint64_t v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// Called by ONE thread.  Returns the exclusive prefix of tile `t` (0 when `first`), publishes the inclusive one.
+__device__ uint64_t lookback(uint64_t *states, uint32_t t, bool first, uint64_t aggregate) {
+	aggregate &= LB_MASK;
+	if(first) { lb_store(states + t, LB_PFX | aggregate); return 0; }
+	lb_store(states + t, LB_AGG | aggregate);
+	uint64_t excl = 0;
+	uint32_t p = t - 1;
+	for(;;) {
+		uint64_t s = lb_load(states + p);
+		uint64_t flag = s >> 62;
+		if(flag == 0) continue;
+		excl += s & LB_MASK;
+		if(flag == 2) break;
+		p--;
+	}
+	excl &= LB_MASK;
+	lb_store(states + t, LB_PFX | ((excl + aggregate) & LB_MASK));
+	return excl;
+}
+
+// exclusive scan of one u32 per thread across a 256-thread CTA; returns the exclusive prefix, total in *total.
+__device__ __forceinline__ uint32_t cta_scan_excl_256(uint32_t v, uint32_t *s_warp /*[9]*/, uint32_t *total) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for(int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if(lane >= d) inc += o; }
+	if(lane == 31) s_warp[w] = inc;
+	__syncthreads();
+	if(w == 0) {
+		uint32_t x = lane < 8 ? s_warp[lane] : 0, xi = x;
+#pragma unroll
+		for(int d = 1; d < 8; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, xi, d); if(lane >= d) xi += o; }
+		if(lane < 8) s_warp[lane] = xi - x;
+		if(lane == 7) s_warp[8] = xi;
+	}
+	__syncthreads();
+	uint32_t r = s_warp[w] + inc - v;
+	*total = s_warp[8];
+	__syncthreads();
+	return r;
+}
+
+#define NEXT_TILE(ticket, ntiles, s_tile)                       \
+	if(threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);        \
+	__syncthreads();                                             \
+	const uint32_t tile_id = s_tile;                             \
+	__syncthreads();                                             \
+	if(tile_id >= (uint32_t)(ntiles)) break;
+
+// =========================================================================================================
+// K1  Tunstall dictionaries
+// =========================================================================================================
+__global__ void __launch_bounds__(32) k_tun_tables(DevBatch B) {
+	const int t = blockIdx.x;
+	const TunDesc td = B.tun[t];
+	if(td.raw || td.nsym <= 1) return;
+	__shared__ TunScratch S;
+	__shared__ __align__(16) uint8_t text[TUN_TABLE_BYTES];
+	__shared__ __align__(16) uint32_t entry[256];
+	__shared__ uint8_t probs[512];
+	__shared__ uint32_t s_used;
+	const int lane = threadIdx.x;
+	for(uint32_t i = lane; i < 2*td.nsym; i += 32) probs[i] = B.blobs[td.probs_off + i];
+	__syncwarp();
+	if(lane == 0) s_used = tun_build_seq(probs, td.nsym, S, text, entry);
+	__syncwarp();
+	const uint32_t used16 = (s_used + 15u) & ~15u;
+	uint8_t *rec = B.tunrec + (size_t)t*TUN_REC_BYTES;
+	uint4 *dst = (uint4 *)rec;
+	const uint4 *se = (const uint4 *)entry;
+	for(int i = lane; i < 64; i += 32) dst[i] = se[i];
+	const uint4 *st = (const uint4 *)text;
+	for(uint32_t i = lane; i < used16/16; i += 32) dst[64 + i] = st[i];
+	if(lane == 0) B.tun_used[t] = used16;
+}
+
+// =========================================================================================================
+// K2  Tunstall decode:  out_off[i] = sum_{j<i} len[data[j]];  byte i copies its word;  the last byte of a block
+//     copies exactly the remainder (tunstall.cpp:446-451).  Raw (NONE) and single-symbol blocks are copies/fills.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
+	__shared__ __align__(16) uint32_t s_entry[256];
+	__shared__ __align__(16) uint8_t s_text[TUN_TABLE_BYTES];
+	__shared__ __align__(8) uint64_t s_bar;
+	__shared__ uint32_t s_warp[9];
+	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_base;
+	const int tid = threadIdx.x;
+	if(tid == 0) mbar_init(&s_bar, 1);
+	__syncthreads();
+	uint32_t parity = 0;
+	for(;;) {
+		NEXT_TILE(ticket, ntiles, s_tile)
+		const Tile tl = tiles[tile_id];
+		const TunDesc td = B.tun[tl.a];
+		uint8_t *out = B.symbols + td.out_off;
+		if(td.raw || td.nsym <= 1) {
+			// tile covers TUN_TILE*4 output bytes
+			const uint32_t lo = tl.tile*(TUN_TILE*4u);
+			uint32_t hi = lo + TUN_TILE*4u; if(hi > td.size) hi = td.size;
+			if(td.raw) { const uint8_t *in = B.blobs + td.data_off; for(uint32_t i = lo + tid; i < hi; i += 256) out[i] = in[i]; }
+			else { const uint8_t sym = td.nsym ? B.blobs[td.probs_off] : 0; for(uint32_t i = lo + tid; i < hi; i += 256) out[i] = sym; }
+			continue;
+		}
+		// stage the dictionary (entries + used text) with one TMA bulk copy per part
+		if(tid == 0) {
+			const uint32_t used16 = B.tun_used[tl.a];
+			const uint8_t *rec = B.tunrec + (size_t)tl.a*TUN_REC_BYTES;
+			fence_proxy_async();
+			mbar_expect_tx(&s_bar, 1024u + used16);
+			tma_bulk_g2s(s_entry, rec, 1024u, &s_bar);
+			if(used16) tma_bulk_g2s(s_text, rec + 1024, used16, &s_bar);
+		}
+		// my 8 compressed bytes
+		const uint8_t *in = B.blobs + td.data_off;
+		const uint32_t i0 = tl.tile*TUN_TILE + tid*8u;
+		uint8_t by[8];
+#pragma unroll
+		for(int j = 0; j < 8; j++) by[j] = (i0 + j < td.csize) ? in[i0 + j] : 0;
+		mbar_wait(&s_bar, parity); parity ^= 1;
+		uint32_t mylen = 0;
+#pragma unroll
+		for(int j = 0; j < 8; j++) if(i0 + j < td.csize) mylen += s_entry[by[j]] >> 16;
+		uint32_t total;
+		uint32_t off = cta_scan_excl_256(mylen, s_warp, &total);
+		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
+		__syncthreads();
+		uint64_t o = s_base + off;
+#pragma unroll
+		for(int j = 0; j < 8; j++) {
+			const uint32_t i = i0 + j;
+			if(i >= td.csize) break;
+			const uint32_t e = s_entry[by[j]];
+			const uint32_t st = e & 0xffffu;
+			uint32_t len = e >> 16;
+			if(i == td.csize - 1) len = o < td.size ? (uint32_t)(td.size - o) : 0;   // last byte: the remainder
+			for(uint32_t k = 0; k < len && o + k < td.size; k++) out[o + k] = s_text[(st + k) & (TUN_TABLE_BYTES - 1)];
+			o += len;
+		}
+		__syncthreads();   // everyone done with s_entry/s_text before the next TMA overwrites them
+	}
+}
+
+// =========================================================================================================
+// K3  bit unpack.  Tile = BIT_TILE logs of one component stream.  Chain = all streams of one attribute
+//     (decodeValues: component c's bits follow component c-1's in the same BITS, cstream.h:294-319).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_bit_unpack(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
+	__shared__ uint32_t s_warp[9];
+	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_base;
+	const int tid = threadIdx.x;
+	for(;;) {
+		NEXT_TILE(ticket, ntiles, s_tile)
+		const Tile tl = tiles[tile_id];
+		const MeshDesc *M = B.mesh + tl.a;
+		const int ai = tl.b & 0xff, comp = tl.b >> 8;
+		const AttrDesc *A = &M->attr[ai];
+		const bool correlated = (A->codec == CODEC_NORMAL) || (A->codec == CODEC_GENERIC && (A->strategy & S_CORRELATED));
+		const TunDesc td = B.tun[A->tun[correlated ? 0 : comp]];
+		const uint8_t *logs = B.symbols + td.out_off;
+		const uint32_t i0 = tl.tile*BIT_TILE + tid*4u;
+		const int nc = A->ncomp;
+		uint32_t d[4];
+		if(i0 + 3 < td.size) { uchar4 q = *(const uchar4 *)(logs + i0); d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; }
+		else {
+#pragma unroll
+			for(int j = 0; j < 4; j++) d[j] = (i0 + j < td.size) ? logs[i0 + j] : 0;
+		}
+		const uint32_t mult = correlated ? (uint32_t)nc : 1u;
+		const uint32_t mybits = (d[0] + d[1] + d[2] + d[3])*mult;
+		uint32_t total;
+		uint32_t off = cta_scan_excl_256(mybits, s_warp, &total);
+		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
+		__syncthreads();
+		uint64_t pos = s_base + off;
+		const uint32_t *words = (const uint32_t *)(B.blobs + A->bits_off);
+		const uint32_t nwords = A->bits_nwords;
+		const bool as_u8 = (A->codec == CODEC_COLOR);
+		int32_t *dst32 = (int32_t *)(A->codec == CODEC_NORMAL || as_u8 ? A->work_ptr : A->out_ptr);
+		uint8_t *dst8 = (uint8_t *)A->work_ptr;
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			const uint32_t i = i0 + j;
+			if(i >= td.size) break;
+			const int dd = (int)d[j];
+			const int rd = dd > 32 ? 32 : dd;
+			if(correlated) {
+				const uint32_t bias = array_bias(dd);
+				for(int k = 0; k < nc; k++) {
+					uint32_t v = 0;
+					if(dd) { v = getbits(words, nwords, pos, rd) - bias; pos += (uint64_t)dd; }
+					dst32[(size_t)i*nc + k] = (int32_t)v;
+				}
+			} else {
+				int32_t v = 0;
+				if(dd) { v = fold_value(getbits(words, nwords, pos, rd), dd); pos += (uint64_t)dd; }
+				if(as_u8) dst8[(size_t)i*nc + comp] = (uint8_t)v;
+				else dst32[(size_t)i*nc + comp] = v;
+			}
+		}
+	}
+}
+
+// =========================================================================================================
+// K4  CLERS automaton, v1: one warp per mesh, lane 0 runs the serial machine over global-memory state.
+// =========================================================================================================
+__global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket) {
+	const int lane = threadIdx.x;
+	for(;;) {
+		uint32_t w = 0;
+		if(lane == 0) w = atomicAdd(ticket, 1u);
+		w = __shfl_sync(0xffffffffu, w, 0);
+		if(w >= nwork) break;
+		const uint32_t mi = mesh_order[w];
+		const MeshDesc *M = B.mesh + mi;
+		uint32_t vcount = 0;
+		int rc = 0;
+		if(lane == 0) {
+			const TunDesc td = B.tun[M->clers_tun];
+			ClersIO io;
+			io.clers = B.symbols + td.out_off; io.nclers = td.size;
+			io.split = (const uint32_t *)(B.blobs + M->split_off); io.split_nwords = M->split_nwords;
+			io.group_ends = B.group_ends + M->group0; io.ngroups = M->ngroups;
+			io.nvert = M->nvert; io.nface = M->nface;
+			const size_t slot = blockIdx.x;
+			io.cap = scratch.cap;
+			io.ea = scratch.ea + slot*scratch.cap; io.eb = scratch.eb + slot*scratch.cap;
+			io.order = scratch.order + slot*scratch.cap; io.delayed = scratch.delayed + slot*scratch.cap;
+			uint32_t need = 3u*M->max_group_faces + 3u;
+			if(need < io.cap) io.cap = need;
+			io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
+			io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
+			io.pred = (uint32_t *)M->pred_ptr;
+			rc = clers_decode_seq(io, &vcount);
+			if(rc) B.status[mi] = rc;
+			B.vertex_count[mi] = vcount;
+		}
+		vcount = __shfl_sync(0xffffffffu, vcount, 0);
+		rc = __shfl_sync(0xffffffffu, rc, 0);
+		// vertices the stream never created (corrupt / truncated input): neutral prediction so later passes stay in bounds
+		uint4 *pred = (uint4 *)M->pred_ptr;
+		if(rc) vcount = 0;
+		for(uint32_t v = vcount + lane; v < M->nvert; v += 32) pred[v] = make_uint4(0, 0, 0, 0);
+		__syncwarp();
+	}
+}
+
+// =========================================================================================================
+// K5  mesh delta inverse (serial in vertex order: v[i] depends on earlier vertices chosen by the topology)
+// =========================================================================================================
+__global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work, uint32_t nwork) {
+	const uint32_t w = blockIdx.x;
+	if(w >= nwork) return;
+	const int lane = threadIdx.x;
+	const MeshDesc *M = B.mesh + work[w].x;
+	const AttrDesc *A = &M->attr[work[w].y];
+	if(B.status[work[w].x]) return;
+	const uint32_t nvert = M->nvert;
+	const uint4 *pred = (const uint4 *)M->pred_ptr;
+	const int nc = A->ncomp;
+	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;
+	const bool active = lane < nc;
+	if(A->codec == CODEC_COLOR) {
+		uint8_t *v = (uint8_t *)A->work_ptr;
+		for(uint32_t base = 0; base < nvert; base += 32) {
+			uint4 p = (base + lane < nvert) ? pred[base + lane] : make_uint4(0, 0, 0, 0);
+			const uint32_t cnt = min(32u, nvert - base);
+			for(uint32_t j = 0; j < cnt; j++) {
+				const uint32_t a = __shfl_sync(0xffffffffu, p.x, j), b = __shfl_sync(0xffffffffu, p.y, j), c = __shfl_sync(0xffffffffu, p.z, j);
+				const uint32_t i = base + j;
+				if(i == 0 || !active) continue;
+				uint32_t x = v[(size_t)i*nc + lane];
+				if(par) x = x + v[(size_t)a*nc + lane] + v[(size_t)b*nc + lane] - v[(size_t)c*nc + lane];
+				else x = x + v[(size_t)a*nc + lane];
+				v[(size_t)i*nc + lane] = (uint8_t)x;
+			}
+		}
+	} else {
+		uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
+		for(uint32_t base = 0; base < nvert; base += 32) {
+			uint4 p = (base + lane < nvert) ? pred[base + lane] : make_uint4(0, 0, 0, 0);
+			const uint32_t cnt = min(32u, nvert - base);
+			for(uint32_t j = 0; j < cnt; j++) {
+				const uint32_t a = __shfl_sync(0xffffffffu, p.x, j), b = __shfl_sync(0xffffffffu, p.y, j), c = __shfl_sync(0xffffffffu, p.z, j);
+				const uint32_t i = base + j;
+				if(i == 0 || !active) continue;
+				uint32_t x = v[(size_t)i*nc + lane];
+				if(par) x = x + v[(size_t)a*nc + lane] + v[(size_t)b*nc + lane] - v[(size_t)c*nc + lane];
+				else x = x + v[(size_t)a*nc + lane];
+				v[(size_t)i*nc + lane] = x;
+			}
+		}
+	}
+}
+
+// =========================================================================================================
+// K5'  point-cloud delta inverse: per component running sum  v[i] += v[i-N]  == inclusive scan (wraps)
+//      Tile = SCAN_TILE vertices of one component; chain = (mesh, attr, comp).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_delta_cloud(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
+	__shared__ uint32_t s_warp[9];
+	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_base;
+	const int tid = threadIdx.x;
+	for(;;) {
+		NEXT_TILE(ticket, ntiles, s_tile)
+		const Tile tl = tiles[tile_id];
+		const MeshDesc *M = B.mesh + tl.a;
+		const int ai = tl.b & 0xff, comp = tl.b >> 8;
+		const AttrDesc *A = &M->attr[ai];
+		const int nc = A->ncomp;
+		const uint32_t nvert = M->nvert;
+		const bool as_u8 = (A->codec == CODEC_COLOR);
+		uint32_t *v32 = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
+		uint8_t *v8 = (uint8_t *)A->work_ptr;
+		const uint32_t i0 = tl.tile*SCAN_TILE + tid*4u;
+		uint32_t x[4];
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			const uint32_t i = i0 + j;
+			x[j] = (i < nvert) ? (as_u8 ? (uint32_t)v8[(size_t)i*nc + comp] : v32[(size_t)i*nc + comp]) : 0u;
+		}
+		x[1] += x[0]; x[2] += x[1]; x[3] += x[2];
+		uint32_t total;
+		uint32_t off = cta_scan_excl_256(x[3], s_warp, &total);
+		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
+		__syncthreads();
+		const uint32_t add = (uint32_t)s_base + off;
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			const uint32_t i = i0 + j;
+			if(i >= nvert) break;
+			if(as_u8) v8[(size_t)i*nc + comp] = (uint8_t)(x[j] + add);
+			else v32[(size_t)i*nc + comp] = x[j] + add;
+		}
+	}
+}
+
+// =========================================================================================================
+// K6  normal estimation (ESTIMATED / BORDER).  The reference adds face normals to their three vertices in FACE
+//     ORDER in fp32 (normal_attribute.cpp:44-55); fp32 addition is not associative, so instead of float atomics
+//     each vertex gathers its incident faces through a CSR built here and adds them in ascending face index:
+//     bit-identical to the sequential loop for every input, no exactness guard needed.
+//     csr scratch per mesh (u32 words, zeroed per decode): deg[nvert+1] | cur[nvert] | bnd[nvert] | cidx[nvert+1];  adj[3*nface] apart
+// =========================================================================================================
+struct CsrView { uint32_t *deg, *cur, *bnd, *cidx, *adj; };
+__device__ __forceinline__ CsrView csr_view(const MeshDesc *M) {
+	CsrView c;
+	uint32_t *p = (uint32_t *)M->csr_ptr;
+	c.deg = p; p += M->nvert + 1;
+	c.cur = p; p += M->nvert;
+	c.bnd = p; p += M->nvert;
+	c.cidx = p;
+	c.adj = (uint32_t *)M->adj_ptr;
+	return c;
+}
+__device__ __forceinline__ void load_face(const MeshDesc *M, uint32_t f, uint32_t &a, uint32_t &b, uint32_t &c) {
+	if(M->index16) { const uint16_t *x = (const uint16_t *)M->face_ptr + (size_t)f*3; a = x[0]; b = x[1]; c = x[2]; }
+	else { const uint32_t *x = (const uint32_t *)M->face_ptr + (size_t)f*3; a = x[0]; b = x[1]; c = x[2]; }
+}
+
+// tiles: a = mesh, tile = block of SCAN_TILE faces
+__global__ void __launch_bounds__(256) k_csr_count(DevBatch B, const Tile *tiles, uint32_t ntiles) {
+	const Tile tl = tiles[blockIdx.x];
+	const MeshDesc *M = B.mesh + tl.a;
+	if(B.status[tl.a]) return;
+	const CsrView C = csr_view(M);
+	const bool border = M->attr[M->normal_attr].prediction == N_BORDER;
+	for(uint32_t f = tl.tile*SCAN_TILE + threadIdx.x; f < min(M->nface, (tl.tile + 1)*SCAN_TILE); f += 256) {
+		uint32_t a, b, c;
+		load_face(M, f, a, b, c);
+		if(a >= M->nvert || b >= M->nvert || c >= M->nvert) continue;
+		atomicAdd(C.deg + a, 1u); atomicAdd(C.deg + b, 1u); atomicAdd(C.deg + c, 1u);
+		if(border) { atomicXor(C.bnd + a, b ^ c); atomicXor(C.bnd + b, c ^ a); atomicXor(C.bnd + c, a ^ b); }   // markBoundary :24-37
+	}
+}
+
+// generic exclusive scan of u32 per mesh over nvert+1 elements (element nvert counts 0, so slot nvert receives the
+// total).  mode 0: deg -> deg in place;  mode 1: (bnd != 0) -> cidx.  tiles cover nvert+1 elements.
+__global__ void __launch_bounds__(256) k_scan_u32(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int mode) {
+	__shared__ uint32_t s_warp[9];
+	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_base;
+	const int tid = threadIdx.x;
+	for(;;) {
+		NEXT_TILE(ticket, ntiles, s_tile)
+		const Tile tl = tiles[tile_id];
+		const MeshDesc *M = B.mesh + tl.a;
+		const CsrView C = csr_view(M);
+		const uint32_t n = M->nvert;
+		const uint32_t i0 = tl.tile*SCAN_TILE + tid*4u;
+		uint32_t x[4];
+#pragma unroll
+		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; x[j] = (i < n) ? (mode == 0 ? C.deg[i] : (C.bnd[i] != 0u ? 1u : 0u)) : 0u; }
+		const uint32_t s1 = x[0], s2 = s1 + x[1], s3 = s2 + x[2], s4 = s3 + x[3];
+		uint32_t total;
+		uint32_t off = cta_scan_excl_256(s4, s_warp, &total);
+		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
+		__syncthreads();
+		const uint32_t base = (uint32_t)s_base + off;
+		uint32_t *dst = mode == 0 ? C.deg : C.cidx;
+		const uint32_t e[4] = { base, base + s1, base + s2, base + s3 };
+#pragma unroll
+		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; if(i <= n) dst[i] = e[j]; }
+	}
+}
+
+__global__ void __launch_bounds__(256) k_csr_fill(DevBatch B, const Tile *tiles, uint32_t ntiles) {
+	const Tile tl = tiles[blockIdx.x];
+	const MeshDesc *M = B.mesh + tl.a;
+	if(B.status[tl.a]) return;
+	const CsrView C = csr_view(M);
+	for(uint32_t f = tl.tile*SCAN_TILE + threadIdx.x; f < min(M->nface, (tl.tile + 1)*SCAN_TILE); f += 256) {
+		uint32_t v[3];
+		load_face(M, f, v[0], v[1], v[2]);
+		if(v[0] >= M->nvert || v[1] >= M->nvert || v[2] >= M->nvert) continue;
+#pragma unroll
+		for(int k = 0; k < 3; k++) { const uint32_t s = C.deg[v[k]] + atomicAdd(C.cur + v[k], 1u); C.adj[s] = f; }
+	}
+}
+
+// one thread per vertex; tiles: a = mesh, tile = block of SCAN_TILE vertices
+__global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile *tiles, uint32_t ntiles) {
+	const Tile tl = tiles[blockIdx.x];
+	const MeshDesc *M = B.mesh + tl.a;
+	if(B.status[tl.a]) return;
+	const CsrView C = csr_view(M);
+	const AttrDesc *A = &M->attr[M->normal_attr];
+	const int32_t *P = (const int32_t *)M->attr[M->position_attr].out_ptr;   // still integer (decoder.cpp:191-195)
+	const int32_t *diffs = (const int32_t *)A->work_ptr;
+	const int unit = f2i_x86(A->q);
+	const bool border = A->prediction == N_BORDER;
+	for(uint32_t i = tl.tile*SCAN_TILE + threadIdx.x; i < min(M->nvert, (tl.tile + 1)*SCAN_TILE); i += 256) {
+		const uint32_t beg = C.deg[i], end = C.deg[i + 1];
+		float ex = 0.f, ey = 0.f, ez = 0.f;
+		// incident faces in ascending face index: repeated "smallest face id greater than the last one"
+		uint32_t done = 0;
+		int64_t last = -1;
+		while(done < end - beg) {
+			uint32_t fmin = 0xffffffffu, mult = 0;
+			for(uint32_t s = beg; s < end; s++) {
+				const uint32_t f = C.adj[s];
+				if((int64_t)f > last) { if(f < fmin) { fmin = f; mult = 1; } else if(f == fmin) mult++; }
+			}
+			if(mult == 0) break;
+			uint32_t a, b, c;
+			load_face(M, fmin, a, b, c);
+			const float v0x = i2f(P[(size_t)a*3]), v0y = i2f(P[(size_t)a*3 + 1]), v0z = i2f(P[(size_t)a*3 + 2]);
+			const float ax = f_sub(i2f(P[(size_t)b*3]), v0x), ay = f_sub(i2f(P[(size_t)b*3 + 1]), v0y), az = f_sub(i2f(P[(size_t)b*3 + 2]), v0z);
+			const float bx = f_sub(i2f(P[(size_t)c*3]), v0x), by = f_sub(i2f(P[(size_t)c*3 + 1]), v0y), bz = f_sub(i2f(P[(size_t)c*3 + 2]), v0z);
+			const float nx = f_sub(f_mul(ay, bz), f_mul(az, by));       // point.h:113-115
+			const float ny = f_sub(f_mul(az, bx), f_mul(ax, bz));
+			const float nz = f_sub(f_mul(ax, by), f_mul(ay, bx));
+			for(uint32_t m = 0; m < mult; m++) { ex = f_add(ex, nx); ey = f_add(ey, ny); ez = f_add(ez, nz); }
+			done += mult;
+			last = (int64_t)fmin;
+		}
+		if(!border || C.bnd[i] != 0u) {                               // computeNormals :288-293 / :315-319
+			int32_t qx, qy;
+			to_octa(ex, ey, ez, unit, qx, qy);
+			const uint32_t k = border ? C.cidx[i] : i;
+			int32_t dx = 0, dy = 0;
+			if(k < A->count) { dx = diffs[(size_t)k*2]; dy = diffs[(size_t)k*2 + 1]; }
+			int32_t sx = (int32_t)((uint32_t)qx + (uint32_t)dx), sy = (int32_t)((uint32_t)qy + (uint32_t)dy);
+			float nx, ny, nz;
+			if(A->out_format == F_FLOAT) {
+				to_sphere(sx, sy, unit, nx, ny, nz);
+				float *o = (float *)A->out_ptr + (size_t)i*3;
+				o[0] = nx; o[1] = ny; o[2] = nz;
+			} else {
+				to_sphere((int32_t)(int16_t)sx, (int32_t)(int16_t)sy, unit, nx, ny, nz);    // Point2s truncation, :293
+				int16_t *o = (int16_t *)A->out_ptr + (size_t)i*3;
+				o[0] = f2s_x86(f_mul(nx, 32767.0f)); o[1] = f2s_x86(f_mul(ny, 32767.0f)); o[2] = f2s_x86(f_mul(nz, 32767.0f));
+			}
+		} else if(A->out_format == F_FLOAT) {                         // interior vertex, no correction :320-322
+			const float len = f_norm3(ex, ey, ez);
+			float *o = (float *)A->out_ptr + (size_t)i*3;
+			o[0] = f_div(ex, len); o[1] = f_div(ey, len); o[2] = f_div(ez, len);
+		} else {                                                      // :294-302; tiny normal leaves the output untouched (H10)
+			float len = f_norm3(ex, ey, ez);
+			if(!(len < 0.00001f)) {
+				len = f_div(32767.0f, len);
+				int16_t *o = (int16_t *)A->out_ptr + (size_t)i*3;
+				o[0] = f2s_x86(f_mul(ex, len)); o[1] = f2s_x86(f_mul(ey, len)); o[2] = f2s_x86(f_mul(ez, len));
+			}
+		}
+	}
+}
+
+// =========================================================================================================
+// K7  dequantise.  tiles: a = mesh, b = attr, tile = block of SCAN_TILE vertices
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_dequant(DevBatch B, const Tile *tiles, uint32_t ntiles) {
+	const Tile tl = tiles[blockIdx.x];
+	const MeshDesc *M = B.mesh + tl.a;
+	if(B.status[tl.a]) return;
+	const AttrDesc *A = &M->attr[tl.b];
+	const uint32_t v0 = tl.tile*SCAN_TILE, v1 = min(M->nvert, v0 + SCAN_TILE);
+	if(A->codec == CODEC_GENERIC) {
+		const int nc = A->ncomp;
+		const float q = A->q;
+		if(A->out_format == F_FLOAT) {
+			int32_t *v = (int32_t *)A->out_ptr;
+			float *o = (float *)A->out_ptr;
+			for(size_t i = (size_t)v0*nc + threadIdx.x; i < (size_t)v1*nc; i += 256) o[i] = f_mul(i2f(v[i]), q);      // vertex_attribute.h:190-193
+		} else {
+			uint32_t *v = (uint32_t *)A->out_ptr;
+			for(size_t i = (size_t)v0*nc + threadIdx.x; i < (size_t)v1*nc; i += 256) v[i] = f2u_x86(f_mul(__uint2float_rn(v[i]), q));   // :200-203
+		}
+	} else if(A->codec == CODEC_NORMAL) {                             // DIFF only, normal_attribute.cpp:257-279
+		const int32_t *d = (const int32_t *)A->work_ptr;
+		const int unit = f2i_x86(A->q);
+		for(uint32_t i = v0 + threadIdx.x; i < v1; i += 256) {
+			float nx, ny, nz;
+			if(A->out_format == F_FLOAT) {
+				to_sphere(d[(size_t)i*2], d[(size_t)i*2 + 1], unit, nx, ny, nz);
+				float *o = (float *)A->out_ptr + (size_t)i*3;
+				o[0] = nx; o[1] = ny; o[2] = nz;
+			} else {
+				to_sphere((int32_t)(int16_t)d[(size_t)i*2], (int32_t)(int16_t)d[(size_t)i*2 + 1], unit, nx, ny, nz);
+				int16_t *o = (int16_t *)A->out_ptr + (size_t)i*3;
+				o[0] = f2s_x86(f_mul(nx, 32767.0f)); o[1] = f2s_x86(f_mul(ny, 32767.0f)); o[2] = f2s_x86(f_mul(nz, 32767.0f));
+			}
+		}
+	} else {                                                          // colour: YCC -> RGB, scale (color_attribute.cpp:76-95, point.h:214)
+		const int nc = A->ncomp, oc = A->out_components;
+		const uint8_t *y = (const uint8_t *)A->work_ptr;
+		uint8_t *o = (uint8_t *)A->out_ptr;
+		for(uint32_t i = v0 + threadIdx.x; i < v1; i += 256) {
+			uint32_t c[4] = {0, 0, 0, 255};
+			for(int k = 0; k < nc; k++) c[k] = y[(size_t)i*nc + k];
+			const uint32_t rgb[4] = { (c[2] + c[0]) & 255u, c[0], (c[1] + c[0]) & 255u, c[3] };
+			for(int k = 0; k < oc; k++) o[(size_t)i*oc + k] = (uint8_t)(rgb[k]*(uint32_t)A->qc[k]);
+		}
+	}
+}
+
+// =========================================================================================================
+// launchers
+// =========================================================================================================
+static inline uint32_t persistent_grid(uint32_t ntiles, int per_sm, int sms) {
+	uint32_t g = (uint32_t)(per_sm*sms);
+	return ntiles < g ? ntiles : g;
+}
+
+#define LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if(e__ != cudaSuccess) return (int)e__; } while(0)
+
+int launch_tun_tables(const DevBatch &B, int ntun, cudaStream_t s) {
+	if(ntun == 0) return 0;
+	k_tun_tables<<<ntun, 32, 0, s>>>(B);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_tun_decode(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_tun_decode<<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_bit_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_bit_unpack<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, cudaStream_t s) {
+	if(nwork == 0) return 0;
+	uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
+	k_clers<<<g, 32, 0, s>>>(B, order, nwork, scratch, ticket);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cudaStream_t s) {
+	if(nwork == 0) return 0;
+	k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_delta_cloud(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_delta_cloud<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_csr_count(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_csr_count<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int mode, int sms, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_scan_u32<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket, mode);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_csr_fill(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_csr_fill<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_normal_estimate<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_dequant<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	LAUNCH_CHECK(); return 0;
+}
+
+}  // namespace crtb

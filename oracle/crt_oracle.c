@@ -110,7 +110,7 @@ typedef struct {
 static void tun_build(Tun *t) {
 	const uint32_t n = (uint32_t)t->nsym;
 	if(n <= 1) return;                               /* tunstall.cpp:127 */
-	uint32_t qprob[1024];
+	uint32_t qprob[1024] = {0};
 	int *widx = t->index, *wlen = t->length;         /* slot -> (offset,len); compacted in place at the end */
 	uint32_t head[256];
 	uint8_t *buf = t->table;

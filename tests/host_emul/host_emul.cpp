@@ -1,0 +1,60 @@
+// tests/host_emul/host_emul.cpp — CPU exercise of the __host__ __device__ cores the kernels run
+// (corto_b200/csrc/crt_device.cuh) plus the host directory walk, so their logic is checked without a GPU.
+// Built and driven by tests/test_host_emul.py; compares against the oracle from Python.  Not part of the product.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../corto_b200/csrc/crt_device.cuh"
+#include "../../corto_b200/csrc/crt_walk.h"
+#include "../../include/corto_b200.h"
+
+using namespace crtb;
+
+extern "C" {
+
+// Tunstall dictionary through tun_build_seq: index[256], lengths[256], text[8192]; returns used bytes.
+int emul_tunstall_tables(const uint8_t *probs, int nsym, int *index256, int *lengths256, uint8_t *text8192) {
+	static TunScratch S;
+	static uint32_t entry[256];
+	memset(text8192, 0, 8192);
+	uint32_t used = tun_build_seq(probs, (uint32_t)nsym, S, text8192, entry);
+	for(int i = 0; i < 256; i++) { index256[i] = (int)(entry[i] & 0xffff); lengths256[i] = (int)(entry[i] >> 16); }
+	return (int)used;
+}
+
+// Walk a blob and return every entropy block's (probs_off, nsym, size, csize, data_off) — 5 u32 per block.
+int emul_walk_blocks(const uint8_t *blob, int len, uint32_t *out, int cap) {
+	ParsedMesh pm; std::string err;
+	if(parse_header(blob, len, pm, err) || walk_directory(pm, err)) return -1;
+	int n = 0;
+	auto put = [&](const Block &b) { if(n < cap) { uint32_t *o = out + n*5; o[0] = b.probs_off; o[1] = b.nsym; o[2] = b.size; o[3] = b.csize; o[4] = b.data_off; } n++; };
+	if(pm.nface) put(pm.clers);
+	for(auto &s: pm.streams) for(auto &b: s.blocks) put(b);
+	return n;
+}
+
+// CLERS automaton through clers_decode_seq given the decoded cler bytes (from the oracle); outputs faces (u32)
+// and prediction (3 u32 per vertex).  Returns the automaton's return code.
+int emul_clers(const uint8_t *blob, int len, const uint8_t *clers, uint32_t nclers, uint32_t *faces, uint32_t *prediction) {
+	ParsedMesh pm; std::string err;
+	if(parse_header(blob, len, pm, err) || walk_directory(pm, err)) return -100;
+	uint32_t maxg = 0, prev = 0;
+	for(uint32_t e: pm.group_ends) { if(e > prev && e - prev > maxg) maxg = e - prev; prev = e; }
+	uint32_t cap = 3*maxg + 16;
+	std::vector<EdgeA> ea(cap); std::vector<EdgeB> eb(cap); std::vector<uint32_t> order(cap), delayed(cap), pred((size_t)pm.nvert*4 + 4);
+	ClersIO io;
+	io.clers = clers; io.nclers = nclers;
+	io.split = (const uint32_t *)(blob + pm.split_off); io.split_nwords = pm.split_nwords;
+	io.group_ends = pm.group_ends.data(); io.ngroups = (uint32_t)pm.group_ends.size();
+	io.nvert = pm.nvert; io.nface = pm.nface;
+	io.ea = ea.data(); io.eb = eb.data(); io.order = order.data(); io.delayed = delayed.data(); io.cap = cap;
+	io.faces32 = faces; io.faces16 = nullptr; io.pred = pred.data();
+	uint32_t vc = 0;
+	int rc = clers_decode_seq(io, &vc);
+	for(uint32_t v = 0; v < pm.nvert; v++) for(int k = 0; k < 3; k++) prediction[v*3 + k] = pred[(size_t)v*4 + k];
+	return rc;
+}
+
+}

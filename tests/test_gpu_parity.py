@@ -1,0 +1,96 @@
+"""GPU parity: CUDA path (through the C ABI) vs the oracle, bit for bit, on every fixture category.
+
+`-m gpu`.  Ground truth = oracle/liboracle.so (pinned to the reference by tests/test_oracle.py) and, when the prebuilt
+reference shim travelled with the snapshot, the unmodified reference itself.
+"""
+import numpy as np
+import pytest
+
+import corto_b200
+from tests import cases
+from oracle import pyoracle, refshim
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(name, a, b):
+    assert a.shape == b.shape and a.dtype == b.dtype, (name, a.shape, b.shape, a.dtype, b.dtype)
+    av, bv = a.reshape(a.shape[0], -1).view(np.uint8), b.reshape(b.shape[0], -1).view(np.uint8)
+    if not np.array_equal(av, bv):
+        bad = np.nonzero((av != bv).any(1))[0]
+        raise AssertionError("%s: %d of %d rows differ, first %d: got %s want %s" % (name, len(bad), a.shape[0], bad[0], a[bad[0]], b[bad[0]]))
+
+
+def _check_blob(blob, tag):
+    info = pyoracle.info(blob)
+    for var in cases.VARIANTS:
+        if not cases.applicable(var, info["attrs"], info["nvert"], info["nface"]):
+            continue
+        want = pyoracle.decode(blob, **var)
+        kw = dict(index16=var.get("index16", False), normals16=var.get("normals16", False), color_components=var.get("color_out"))
+        got = corto_b200.Decoder(blob).decode(**kw)
+        for k, w in want.items():
+            if isinstance(w, np.ndarray):
+                _same("%s%s/%s" % (tag, var, k), got[k], w)
+        if refshim.available():
+            r = refshim.decode(blob, **var)
+            for k, w in r.items():
+                if isinstance(w, np.ndarray):
+                    _same("%s%s/%s(ref)" % (tag, var, k), got[k], w)
+
+
+@pytest.mark.parametrize("name,builder", cases.SMALL, ids=[c[0] for c in cases.SMALL])
+def test_small(name, builder):
+    if not refshim.available():
+        pytest.skip("needs the reference shim to encode")
+    _check_blob(builder(), name)
+
+
+@pytest.mark.parametrize("name,builder", cases.MEDIUM, ids=[c[0] for c in cases.MEDIUM])
+def test_medium(name, builder):
+    if not refshim.available():
+        pytest.skip("needs the reference shim to encode")
+    _check_blob(builder(), name)
+
+
+def test_batch_mixed():
+    """All small + medium blobs in ONE device-resident batch; every mesh's slices must match the oracle."""
+    if not refshim.available():
+        pytest.skip("needs the reference shim to encode")
+    import torch
+    blobs = [b() for _, b in cases.SMALL + cases.MEDIUM]
+    blobs = [b for b in blobs if len([a for a in pyoracle.info(b)["attrs"] if a["name"] == "radius"]) == 0]
+    bd = corto_b200.BatchDecoder(blobs, color_components=4)
+    bd.allocate(fill=0xA5)
+    bd.upload()
+    bd.decode()
+    torch.cuda.synchronize()
+    rc, st = bd.status()
+    assert rc == 0, st
+    for i, blob in enumerate(blobs):
+        want = pyoracle.decode(blob, color_out=4)
+        got = bd.mesh_outputs(i)
+        for k, w in want.items():
+            if isinstance(w, np.ndarray):
+                _same("batch[%d]/%s" % (i, k), got[k], w)
+    # second decode of the same batch object must give the same answer (scratch / tickets reset correctly)
+    bd.decode()
+    torch.cuda.synchronize()
+    for i in (0, len(blobs) - 1):
+        want = pyoracle.decode(blobs[i], color_out=4)
+        got = bd.mesh_outputs(i)
+        for k, w in want.items():
+            if isinstance(w, np.ndarray):
+                _same("batch2[%d]/%s" % (i, k), got[k], w)
+
+
+def test_tarta():
+    import os
+    if not os.path.exists(refshim.TARTA):
+        pytest.skip("tarta.crt fixture not present")
+    blob = refshim.aligned_blob(open(refshim.TARTA, "rb").read())
+    want = pyoracle.decode(blob)
+    got = corto_b200.Decoder(blob).decode()
+    for k, w in want.items():
+        if isinstance(w, np.ndarray):
+            _same("tarta/" + k, got[k], w)
