@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — decoded MVerts/s of batched .crt decode on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--batch 256] [--impl ours|reference]
+
+A "step" is one pass of the decode hot path over one batch of synthetic meshes (BASELINE configs[1]: 256 x 128K-vertex
+pos14/uv12/normal10 meshes per GPU).  Work shards by mesh: every rank decodes its own batch (weak scaling), there is no
+data-path collective; torch.distributed is used only for the barrier and the max-over-ranks time.
+
+  value     verts decoded by all ranks / max-over-ranks device time, blobs already resident in HBM, outputs left in HBM.
+            The host directory walk (O(#blocks), microseconds per mesh) + its H2D is re-done INSIDE every timed step.
+  e2e       same metric through the public API with HOST buffers: H2D of the blobs from pinned memory, kernels,
+            D2H of every output arena into pinned memory, all inside the timed region.
+  roofline  dominant kernel (by measured device time): algorithmic bytes (blob + bound outputs) / its mean
+            duration (CUDA events on the launch stream, inside the timed region) against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores, rank 0, N=1 only.
+
+`--impl reference` times the reference's own single-threaded C++ decoder, one Decoder per host thread over all host
+threads, on the same workload (bounded sample per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    p.add_argument("--batch", type=int, default=None, help="meshes per GPU (default: 256 for c2, 512 c3, 512 c4, 1 c1/c5)")
+    p.add_argument("--distinct", type=int, default=None, help="distinct seeds to encode (default: all)")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    return p.parse_args()
+
+
+DEFAULT_BATCH = dict(c1=1, c2=256, c3=512, c4=512, c5=1)
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def algorithmic_bytes(bd):
+    """len(blob) + every bound output array."""
+    out = sum(int(t.numel()) * t.element_size() for t in bd.out.values())
+    return int(bd.total_bytes), out
+
+
+def run_reference(args, rank, world, blobs):
+    """Reference arm: the unmodified reference's CPU decode, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import refshim, pyoracle
+    threads = os.cpu_count() or 1
+    sample = blobs[:max(1, min(len(blobs), 4 * threads))]
+    verts = sum(pyoracle.info(b)["nvert"] for b in sample)
+    kind = "reference" if refshim.available() else "port"
+
+    def one():
+        if kind == "reference":
+            return refshim.decode_bench(sample, threads, 1)
+        t0 = time.perf_counter()
+        pyoracle.decode_all(sample)
+        return time.perf_counter() - t0
+    for _ in range(args.warmup):
+        one()
+    ts = [one() for _ in range(args.steps)]
+    total = sum(ts)
+    val = verts * args.steps / total / 1e6
+    desc = "%d of %d meshes per step" % (len(sample), len(blobs))
+    print(json.dumps({
+        "impl": "reference", "metric": "decoded MVerts/s (batched .crt)", "value": val, "unit": "MVerts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME(args), "batch_per_gpu": len(blobs), "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "MVerts/s", "cores": threads if kind == "reference" else 1, "kind": kind, "sample": desc},
+        "e2e": {"value": val, "unit": "MVerts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def WORKLOAD_NAME(args):
+    from oracle import workloads
+    return "%s: %s" % (args.workload, workloads.DESCRIPTION[args.workload])
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    batch = args.batch or DEFAULT_BATCH[args.workload]
+
+    from oracle import workloads, refshim
+    if args.impl == "reference":
+        if rank == 0:
+            blobs = workloads.build(args.workload, batch, seed0=1, distinct=args.distinct or min(batch, 32))
+            run_reference(args, rank, world, blobs)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import corto_b200
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # ---- synthetic batch for this rank (different seeds per rank): set-up, not timed -------------------------------
+    blobs = workloads.build(args.workload, batch, seed0=1 + rank * batch, distinct=args.distinct)
+    # one pinned host buffer holds every blob (16-byte aligned slices): the e2e leg's H2D source
+    offs, tot = [], 0
+    for b in blobs:
+        offs.append(tot)
+        tot += (len(b) + 15) // 16 * 16
+    pinned = torch.empty(tot + 16, dtype=torch.uint8).pin_memory()
+    pn = pinned.numpy()
+    base = (-pn.ctypes.data) % 16
+    views = []
+    for b, o in zip(blobs, offs):
+        v = pn[base + o: base + o + len(b)]
+        v[:] = b
+        views.append(v)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident decode: `value` ---------------------------------------------------------------------------
+    bd = corto_b200.BatchDecoder(views)
+    bd.allocate()
+    bd.upload()
+    bd.set_profiling(True)
+    for _ in range(max(args.warmup, 3)):
+        bd.rewalk(); bd.decode()
+    torch.cuda.synchronize()
+    rc, st = bd.status()
+    assert rc == 0, "decode failed: %s" % corto_b200.lib().crt_last_error()
+    in_bytes, out_bytes = algorithmic_bytes(bd)
+    sampler = ClockSampler(local)
+    stage_acc = {}
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    per_step_stage = []
+    for _ in range(args.steps):
+        bd.rewalk()          # host directory walk + H2D of the directory: part of Decoder::decode, so part of the step
+        bd.decode()
+        # stage events are re-recorded every step; read them lazily after a sync of this step only when cheap
+        torch.cuda.current_stream().synchronize()
+        per_step_stage.append(bd.stage_times())
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    tms = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    total_verts = bd.total_verts * world
+    value = total_verts * args.steps / (ms_max * 1e-3) / 1e6
+    for st_ in per_step_stage:
+        for name, t in st_:
+            stage_acc.setdefault(name, []).append(t)
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else None
+    peak, peak_src = peaks()
+    roof = None
+    if dom:
+        ach = (in_bytes + out_bytes) / (stage_ms[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
+                "algorithmic_bytes": {"blobs": in_bytes, "outputs": out_bytes},
+                "step_achieved": (in_bytes + out_bytes) * args.steps / (ms * 1e-3) / 1e9,
+                "read_only_frac": in_bytes / (stage_ms[dom] * 1e-3) / 1e9 / peak,
+                "note": "latency-bound serial CLERS automaton dominates mesh decode; see DESIGN.md"}
+    launches = bd.launches * args.steps
+
+    # ---- end to end through the public API with host buffers ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in bd.out.items()}
+        d2h = sum(int(t.numel()) * t.element_size() for t in host_out.values())
+
+        def e2e_step():
+            bd.upload()                                   # directory walk + H2D of blobs (pinned) and tables
+            bd.decode()
+            for k, v in bd.out.items():
+                host_out[k].copy_(v, non_blocking=True)   # D2H of every output arena
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ke = max(2, min(args.steps, 5))
+        for _ in range(ke):
+            e2e_step()
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_verts * ke / (float(ems.item()) * 1e-3) / 1e6, "unit": "MVerts/s", "h2d_bytes_per_step": int(in_bytes),
+               "d2h_bytes_per_step": int(d2h), "steps": ke}
+
+    # ---- CPU baseline beside it (rank 0, N=1) -----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import pyoracle
+        sample = blobs[:min(len(blobs), 64)]
+        sv = sum(pyoracle.info(b)["nvert"] for b in sample)
+        if refshim.available():
+            t1 = refshim.decode_bench(sample, 1, 3)
+            tall = refshim.decode_bench(sample, os.cpu_count() or 1, 3)
+            cpu = {"value": sv / t1 / 1e6, "unit": "MVerts/s", "cores": 1, "kind": "reference",
+                   "sample": "%d of %d meshes, best of 3 passes, Decoder ctor+set*+decode()" % (len(sample), len(blobs)),
+                   "all_cores": {"value": sv / tall / 1e6, "cores": os.cpu_count()}}
+        else:
+            t0 = time.perf_counter(); pyoracle.decode_all(sample); t1 = time.perf_counter() - t0
+            cpu = {"value": sv / t1 / 1e6, "unit": "MVerts/s", "cores": 1, "kind": "port", "sample": "%d of %d meshes, 1 pass" % (len(sample), len(blobs))}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "decoded MVerts/s (batched .crt)", "value": value, "unit": "MVerts/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+fp32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME(args), "batch_per_gpu": batch, "verts_per_gpu": int(bd.total_verts),
+                       "faces_per_gpu": int(bd.total_faces), "blob_bytes_per_gpu": int(in_bytes), "output_bytes_per_gpu": int(out_bytes),
+                       "parallelism": "mesh-sharded x%d, no data-path collective" % world,
+                       "l2": "inputs+outputs (%.2f GB) larger than the 126 MB L2; no explicit flush" % ((in_bytes + out_bytes) / 1e9),
+                       "timed_region": "host directory walk + H2D directory + all decode kernels"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "wall_s": t_wall}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

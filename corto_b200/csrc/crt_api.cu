@@ -328,13 +328,15 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	// ---- blob arena ----
 	uint64_t blobs_bytes = 16;
 	for(auto &m: b->meshes) blobs_bytes += align_up(m.len, 16);
-	if(copy_blobs || !b->d_blobs || b->blobs_bytes < blobs_bytes) {
+	if(!b->d_blobs || b->blobs_bytes < blobs_bytes) {
 		if(b->d_blobs) { cudaFree(b->d_blobs); b->d_blobs = nullptr; }
 		CU(cudaMalloc(&b->d_blobs, blobs_bytes));
 		b->blobs_bytes = blobs_bytes;
+		copy_blobs = true;
+	}
+	if(copy_blobs)
 		for(int i = 0; i < n; i++)
 			CU(cudaMemcpyAsync(b->d_blobs + b->h_mesh[i].blob_off, b->meshes[i].blob, b->meshes[i].len, cudaMemcpyHostToDevice, stream));
-	}
 
 	// ---- scratch arena: symbols | per-mesh work | adj | dictionaries | CLERS slots ----
 	const uint64_t ntun = b->h_tun.size();
