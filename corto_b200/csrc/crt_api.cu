@@ -169,7 +169,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 		td.out_off = symbols_bytes;
 		td.nsym = blk.nsym; td.size = blk.size; td.csize = blk.csize; td.raw = blk.raw ? 1 : 0;
 		td.tile0 = (uint32_t)b->t_tun.size();
-		symbols_bytes += align_up((uint64_t)blk.size + 4, 16);
+		symbols_bytes += align_up((uint64_t)blk.size + 32, 16);   // k_clers reads its symbols through 8-byte windows, 16 bytes ahead
 		const int id = (int)b->h_tun.size();
 		if(blk.size) {
 			if(blk.raw || blk.nsym <= 1) {
@@ -342,7 +342,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	const uint64_t ntun = b->h_tun.size();
 	uint32_t cap = 16, nmesh_faces = (uint32_t)b->clers_order.size();
 	for(auto &M: b->h_mesh) if(M.nface) cap = std::max(cap, 3u*M.max_group_faces + 16u);
-	uint32_t slots = std::min<uint32_t>(nmesh_faces, (uint32_t)b->sms*4u);
+	uint32_t slots = std::min<uint32_t>(nmesh_faces, (uint32_t)b->sms*8u);
 	const uint64_t per_slot = (uint64_t)cap*(sizeof(EdgeA) + sizeof(EdgeB) + 8);
 	while(slots > 1 && per_slot*slots > (48ull << 30)) slots /= 2;
 	uint64_t o_sym = 0, o_work = align_up(o_sym + symbols_bytes + 64, 256), o_adj = align_up(o_work + work_bytes, 256),
@@ -482,7 +482,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_bit_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st, tickets + 1, b->sms, s), !b->t_bits.empty());
 	st += b->t_bits.size();
 	if((rc = mark(b, "bit_unpack", k, s))) return rc;
-	RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, s), !b->clers_order.empty());
+	RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
 	if((rc = mark(b, "clers", k, s))) return rc;
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
 	RUN(launch_delta_cloud(B, t_cloud, (uint32_t)b->t_cloud.size(), st, tickets + 3, b->sms, s), !b->t_cloud.empty());

@@ -365,4 +365,153 @@ CRT_HD int clers_decode_seq(const ClersIO &io, uint32_t *vertex_count_out) {
 	return 0;
 }
 
+
+// ---- CLERS automaton, ring-cached (the kernel's hot version) -----------------------------------------------------
+// Same machine as clers_decode_seq.  The automaton is a pointer chase whose cost is memory latency, so the hot state
+// lives in fast memory (shared memory in k_clers): the most recent R front edges and Q FIFO entries are mirrored in
+// rings indexed by id & (R-1); global memory stays authoritative (write-through) and serves the rare reach-back
+// (99.8 % of front accesses fall within the last 4096 edges).  The edge created last, which is the next
+// one processed 62 % of the time (decoder.cpp:262-264), never leaves registers.  CLERS symbols arrive through a
+// double-buffered 8-byte register window (the stream must be 8-byte aligned and padded by 16 readable bytes).
+struct ClersRing { EdgeA *ra; EdgeB *rb; uint32_t *rq; uint32_t R, Q; };   // R, Q powers of two
+
+CRT_HD uint64_t load_u64(const uint8_t *p) { return *(const uint64_t *)p; }
+
+CRT_HD int clers_decode_ring(const ClersIO &io, const ClersRing &rg, uint32_t *vertex_count_out) {
+	const uint32_t R = rg.R, RM = rg.R - 1, Q = rg.Q, QM = rg.Q - 1;
+	EdgeA *const ra = rg.ra; EdgeB *const rb = rg.rb; uint32_t *const rq = rg.rq;
+	uint32_t cler = 0, vertex_count = 0;
+	uint64_t cw = io.nclers ? load_u64(io.clers) : 0, cw_next = io.nclers > 8 ? load_u64(io.clers + 8) : 0;
+	uint64_t splitpos = 0;
+	const int splitbits = ilog2_u32(io.nvert) + 1;
+	const uint32_t NONE = 0xFFFFFFFFu;
+#define CRT_NEXT_CLER(c)                                                                              \
+	do {                                                                                              \
+		if(cler >= io.nclers) return -5;                                                              \
+		c = (uint32_t)(cw & 0xffu); cw >>= 8; cler++;                                                 \
+		if((cler & 7u) == 0) { cw = cw_next; cw_next = (cler + 8 < io.nclers) ? load_u64(io.clers + cler + 8) : 0; } \
+	} while(0)
+	for(uint32_t g = 0; g < io.ngroups; g++) {
+		uint32_t end = io.group_ends[g]*3;
+		if(end > io.nface*3) end = io.nface*3;
+		uint32_t start = g ? io.group_ends[g - 1]*3 : 0;
+		if(start > io.nface*3) start = io.nface*3;
+		uint32_t nfront = 0, norder = 0, cursor = 0, ndelayed = 0;
+		bool have = false;                 // current edge (the one created last) is held in registers
+		uint32_t cf = 0; EdgeA ce = {0, 0, 0, 0}; EdgeB cl = {0, 0};
+		while(start < end) {
+			if(!have && cursor >= norder && ndelayed == 0) {
+				if(nfront + 3 > io.cap) return -5;
+				uint32_t last = vertex_count - 1;
+				uint32_t vi[3];
+				uint32_t mask = 0, c;
+				CRT_NEXT_CLER(c);
+				if(c == C_SPLIT) { mask = getbits(io.split, io.split_nwords, splitpos, 3); splitpos += 3; }
+				for(int k = 0; k < 3; k++) {
+					uint32_t v;
+					if(mask & (1u << k)) {
+						v = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+						if(v >= io.nvert) return -5;
+					} else {
+						if(vertex_count >= io.nvert) return -5;
+						clers_put_pred(io, vertex_count, last, last, last);
+						last = v = vertex_count++;
+					}
+					vi[k] = v;
+				}
+				clers_put_face(io, start, vi[0], vi[1], vi[2]);
+				start += 3;
+				const uint32_t b = nfront;
+				const EdgeA a0 = {vi[1], vi[2], vi[0], 0}, a1 = {vi[2], vi[0], vi[1], 0}, a2 = {vi[0], vi[1], vi[2], 0};
+				const EdgeB b0 = {b + 2, b + 1}, b1 = {b + 0, b + 2}, b2 = {b + 1, b + 0};
+				io.ea[b] = a0; io.eb[b] = b0; ra[b & RM] = a0; rb[b & RM] = b0;
+				io.ea[b + 1] = a1; io.eb[b + 1] = b1; ra[(b + 1) & RM] = a1; rb[(b + 1) & RM] = b1;
+				io.ea[b + 2] = a2; io.eb[b + 2] = b2; ra[(b + 2) & RM] = a2; rb[(b + 2) & RM] = b2;
+				for(uint32_t k = 0; k < 3; k++) { io.order[norder] = b + k; rq[norder & QM] = b + k; norder++; }
+				nfront += 3;
+				continue;
+			}
+			uint32_t f; EdgeA e; EdgeB el;
+			if(have) { f = cf; e = ce; el = cl; have = false; }
+			else {
+				if(cursor < norder) { f = (cursor + Q >= norder) ? rq[cursor & QM] : io.order[cursor]; cursor++; }
+				else f = io.delayed[--ndelayed];
+				const bool inw = f + R >= nfront;
+				e = inw ? ra[f & RM] : io.ea[f];
+				if(e.deleted) continue;
+				el = inw ? rb[f & RM] : io.eb[f];
+			}
+			uint32_t c;
+			CRT_NEXT_CLER(c);
+			if(c == C_BOUNDARY) continue;
+			if(nfront + 2 > io.cap) return -5;
+			const uint32_t ne = nfront;
+			uint32_t opposite;
+			if(c == C_VERTEX || c == C_SPLIT) {
+				if(c == C_SPLIT) {
+					opposite = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+					if(opposite >= io.nvert) return -5;
+				} else {
+					if(vertex_count >= io.nvert) return -5;
+					clers_put_pred(io, vertex_count, e.v1, e.v0, e.v2);
+					opposite = vertex_count++;
+				}
+				io.eb[el.prev].next = ne;     if(el.prev + R >= ne) rb[el.prev & RM].next = ne;
+				io.eb[el.next].prev = ne + 1; if(el.next + R >= ne) rb[el.next & RM].prev = ne + 1;
+				const EdgeA a0 = {e.v0, opposite, e.v1, 0}, a1 = {opposite, e.v1, e.v0, 0};
+				const EdgeB b0 = {el.prev, ne + 1}, b1 = {ne, el.next};
+				io.ea[ne] = a0; io.eb[ne] = b0; ra[ne & RM] = a0; rb[ne & RM] = b0;
+				io.ea[ne + 1] = a1; io.eb[ne + 1] = b1; ra[(ne + 1) & RM] = a1; rb[(ne + 1) & RM] = b1;
+				io.order[norder] = ne + 1; rq[norder & QM] = ne + 1; norder++;
+				nfront += 2;
+				cf = ne; ce = a0; cl = b0; have = true;
+			} else if(c == C_LEFT) {
+				const uint32_t p = el.prev;
+				const bool pw = p + R >= ne;
+				const EdgeB pl = pw ? rb[p & RM] : io.eb[p];
+				opposite = pw ? ra[p & RM].v0 : io.ea[p].v0;
+				io.ea[p].deleted = 1;         if(pw) ra[p & RM].deleted = 1;
+				io.eb[pl.prev].next = ne;     if(pl.prev + R >= ne) rb[pl.prev & RM].next = ne;
+				io.eb[el.next].prev = ne;     if(el.next + R >= ne) rb[el.next & RM].prev = ne;
+				const EdgeA a0 = {opposite, e.v1, e.v0, 0};
+				const EdgeB b0 = {pl.prev, el.next};
+				io.ea[ne] = a0; io.eb[ne] = b0; ra[ne & RM] = a0; rb[ne & RM] = b0;
+				nfront += 1;
+				cf = ne; ce = a0; cl = b0; have = true;
+			} else if(c == C_RIGHT) {
+				const uint32_t n = el.next;
+				const bool nw = n + R >= ne;
+				const EdgeB nl = nw ? rb[n & RM] : io.eb[n];
+				opposite = nw ? ra[n & RM].v1 : io.ea[n].v1;
+				io.ea[n].deleted = 1;         if(nw) ra[n & RM].deleted = 1;
+				io.eb[nl.next].prev = ne;     if(nl.next + R >= ne) rb[nl.next & RM].prev = ne;
+				io.eb[el.prev].next = ne;     if(el.prev + R >= ne) rb[el.prev & RM].next = ne;
+				const EdgeA a0 = {e.v0, opposite, e.v1, 0};
+				const EdgeB b0 = {el.prev, nl.next};
+				io.ea[ne] = a0; io.eb[ne] = b0; ra[ne & RM] = a0; rb[ne & RM] = b0;
+				nfront += 1;
+				cf = ne; ce = a0; cl = b0; have = true;
+			} else if(c == C_DELAY) {
+				io.delayed[ndelayed++] = f;
+				continue;
+			} else if(c == C_END) {
+				const uint32_t p = el.prev, n = el.next;
+				const bool pw = p + R >= ne, nw = n + R >= ne;
+				const EdgeB pl = pw ? rb[p & RM] : io.eb[p];
+				const EdgeB nl = nw ? rb[n & RM] : io.eb[n];
+				opposite = pw ? ra[p & RM].v0 : io.ea[p].v0;
+				io.ea[p].deleted = 1;         if(pw) ra[p & RM].deleted = 1;
+				io.ea[n].deleted = 1;         if(nw) ra[n & RM].deleted = 1;
+				io.eb[pl.prev].next = nl.next; if(pl.prev + R >= ne) rb[pl.prev & RM].next = nl.next;
+				io.eb[nl.next].prev = pl.prev; if(nl.next + R >= ne) rb[nl.next & RM].prev = pl.prev;
+			} else return -5;
+			clers_put_face(io, start, e.v1, e.v0, opposite);
+			start += 3;
+		}
+	}
+#undef CRT_NEXT_CLER
+	*vertex_count_out = vertex_count;
+	return 0;
+}
+
 }  // namespace crtb

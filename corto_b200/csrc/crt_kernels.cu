@@ -270,9 +270,14 @@ __global__ void __launch_bounds__(256) k_bit_unpack(DevBatch B, const Tile *tile
 }
 
 // =========================================================================================================
-// K4  CLERS automaton, v1: one warp per mesh, lane 0 runs the serial machine over global-memory state.
+// K4  CLERS automaton: one warp per mesh, lane 0 runs the serial machine.  The hot part of its state (last R front
+//     edges, last Q FIFO entries) is cached in shared memory rings, global memory is the write-through backing store.
+//     The automaton is latency-bound (a dependent pointer chase per symbol), so the design goal is the shortest
+//     dependent chain per symbol, not bandwidth: see clers_decode_ring in crt_device.cuh.
 // =========================================================================================================
-__global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket) {
+__global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
+                                              uint32_t R, uint32_t Q) {
+	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int lane = threadIdx.x;
 	for(;;) {
 		uint32_t w = 0;
@@ -299,7 +304,12 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 			io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
 			io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
 			io.pred = (uint32_t *)M->pred_ptr;
-			rc = clers_decode_seq(io, &vcount);
+			ClersRing rg;
+			rg.R = R; rg.Q = Q;
+			rg.ra = (EdgeA *)smem_raw;
+			rg.rb = (EdgeB *)(smem_raw + (size_t)R*sizeof(EdgeA));
+			rg.rq = (uint32_t *)(smem_raw + (size_t)R*(sizeof(EdgeA) + sizeof(EdgeB)));
+			rc = clers_decode_ring(io, rg, &vcount);
 			if(rc) B.status[mi] = rc;
 			B.vertex_count[mi] = vcount;
 		}
@@ -628,10 +638,20 @@ int launch_bit_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 	k_bit_unpack<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, cudaStream_t s) {
+int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
+	// few meshes: big rings (2 CTAs per SM);  many meshes: smaller rings so that more serial chains share an SM
+	uint32_t R = 4096, Q = 2048;
+	if(nwork > (uint32_t)sms*2u) { R = 1024; Q = 1024; }
+	const size_t smem = (size_t)R*(sizeof(EdgeA) + sizeof(EdgeB)) + (size_t)Q*4;
+	static size_t configured = 0;
+	if(configured < smem) {
+		cudaError_t e = cudaFuncSetAttribute(k_clers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return (int)e;
+		configured = smem;
+	}
 	uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
-	k_clers<<<g, 32, 0, s>>>(B, order, nwork, scratch, ticket);
+	k_clers<<<g, 32, smem, s>>>(B, order, nwork, scratch, ticket, R, Q);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cudaStream_t s) {

@@ -37,7 +37,12 @@ int emul_walk_blocks(const uint8_t *blob, int len, uint32_t *out, int cap) {
 
 // CLERS automaton through clers_decode_seq given the decoded cler bytes (from the oracle); outputs faces (u32)
 // and prediction (3 u32 per vertex).  Returns the automaton's return code.
-int emul_clers(const uint8_t *blob, int len, const uint8_t *clers, uint32_t nclers, uint32_t *faces, uint32_t *prediction) {
+// ring_r == 0: clers_decode_seq; else clers_decode_ring with an R = ring_r edge ring and Q = ring_q FIFO ring (tiny rings
+// force the reach-back paths that are rare with the kernel's sizes).
+int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t nclers, uint32_t *faces, uint32_t *prediction, int ring_r, int ring_q) {
+	std::vector<uint8_t> padded((size_t)nclers + 64, 0);
+	memcpy(padded.data() + ((8 - ((uintptr_t)padded.data() & 7)) & 7), clers_in, nclers);
+	const uint8_t *clers = padded.data() + ((8 - ((uintptr_t)padded.data() & 7)) & 7);
 	ParsedMesh pm; std::string err;
 	if(parse_header(blob, len, pm, err) || walk_directory(pm, err)) return -100;
 	uint32_t maxg = 0, prev = 0;
@@ -52,7 +57,13 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers, uint32_t ncle
 	io.ea = ea.data(); io.eb = eb.data(); io.order = order.data(); io.delayed = delayed.data(); io.cap = cap;
 	io.faces32 = faces; io.faces16 = nullptr; io.pred = pred.data();
 	uint32_t vc = 0;
-	int rc = clers_decode_seq(io, &vc);
+	int rc;
+	if(ring_r == 0) rc = clers_decode_seq(io, &vc);
+	else {
+		std::vector<EdgeA> ra(ring_r); std::vector<EdgeB> rb(ring_r); std::vector<uint32_t> rq(ring_q);
+		ClersRing rg{ra.data(), rb.data(), rq.data(), (uint32_t)ring_r, (uint32_t)ring_q};
+		rc = clers_decode_ring(io, rg, &vc);
+	}
 	for(uint32_t v = 0; v < pm.nvert; v++) for(int k = 0; k < 3; k++) prediction[v*3 + k] = pred[(size_t)v*4 + k];
 	return rc;
 }
