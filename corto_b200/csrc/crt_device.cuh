@@ -18,6 +18,9 @@
 
 namespace crtb {
 
+struct uint4_t { uint32_t x, y, z, w; };
+struct uint2_t { uint32_t x, y; };
+
 // ---- exact float helpers -------------------------------------------------------------------------------
 CRT_HD float f_mul(float a, float b) {
 #ifdef __CUDA_ARCH__
@@ -366,43 +369,100 @@ CRT_HD int clers_decode_seq(const ClersIO &io, uint32_t *vertex_count_out) {
 }
 
 
-// ---- CLERS automaton, ring-cached (the kernel's hot version) -----------------------------------------------------
-// Same machine as clers_decode_seq.  The automaton is a pointer chase whose cost is memory latency, so the hot state
-// lives in fast memory (shared memory in k_clers): the most recent R front edges and Q FIFO entries are mirrored in
-// rings indexed by id & (R-1); global memory stays authoritative (write-through) and serves the rare reach-back
-// (99.8 % of front accesses fall within the last 4096 edges).  The edge created last, which is the next
-// one processed 62 % of the time (decoder.cpp:262-264), never leaves registers.  CLERS symbols arrive through a
-// double-buffered 8-byte register window (the stream must be 8-byte aligned and padded by 16 readable bytes).
-struct ClersRing { EdgeA *ra; EdgeB *rb; uint32_t *rq; uint32_t R, Q; };   // R, Q powers of two
-
 CRT_HD uint64_t load_u64(const uint8_t *p) { return *(const uint64_t *)p; }
 
-CRT_HD int clers_decode_ring(const ClersIO &io, const ClersRing &rg, uint32_t *vertex_count_out) {
-	const uint32_t R = rg.R, RM = rg.R - 1, Q = rg.Q, QM = rg.Q - 1;
-	EdgeA *const ra = rg.ra; EdgeB *const rb = rg.rb; uint32_t *const rq = rg.rq;
-	uint32_t cler = 0, vertex_count = 0;
-	uint64_t cw = io.nclers ? load_u64(io.clers) : 0, cw_next = io.nclers > 8 ? load_u64(io.clers + 8) : 0;
-	uint64_t splitpos = 0;
+// ---- CLERS automaton, v3: lazy front + staged outputs (the kernel's hot version) ---------------------------------
+// ncu on a straightforward ring-cached port showed the machine is INSTRUCTION-latency bound: one warp, ~150 dependent
+// instructions per symbol at 4.4-5.6 cycles each, plus L2 round trips whenever the front reaches back past the ring.
+// v3 removes work from the per-symbol chain instead of hiding latency:
+//  * the edge created last is processed next 62 % of the time (decoder.cpp:262-264) and is then never referenced
+//    again, so it lives only in registers: it gets NO id and NO record, and the two links pointing at it are not
+//    written ("deferred": lp = prev's .next, ln = next's .prev) unless the next symbol is BOUNDARY / DELAY, which
+//    materialise it.  Deferred fields are never read while the edge is in flight (LEFT reads prev's .prev/.v0, RIGHT
+//    next's .next/.v1, END both) except in a 2-edge loop, where the edge is materialised first.  Edge ids are
+//    internal (never output), so only materialised edges consume ids: a ring of R slots reaches ~3x further back.
+//  * rings (front edges, FIFO) and outputs (faces, predictions) are written to fast memory only; every `budget`
+//    symbols the WARP (all lanes) drains them to global memory with coalesced stores: faces/predictions as final
+//    outputs, ring entries about to leave the window as the reach-back backing store.  An id below the flushed limit
+//    (eflush / qflush) is served from global memory, anything newer from the ring.
+// Mem policy RG supplies the ring accessors (shared memory in the kernel, plain arrays in tests/host_emul).
+struct ClersState {
+	uint32_t cler, vertex_count;
+	uint64_t cw, cw_next, splitpos;
+	uint32_t g, start, end;            // current group; face cursor / end of group, in FACES
+	uint32_t nfront, norder, cursor, ndelayed;
+	uint32_t have, lp, ln;             // current edge valid; deferred incoming links
+	uint32_t cf, cv0, cv1, cv2, cprev, cnext;   // current edge; cf == CLERS_NOID while it has no record
+	uint32_t eflush, qflush;           // edge ids / FIFO positions below these live in global memory
+	uint32_t fflush, pflush;           // faces / predictions already drained to global memory
+};
+constexpr uint32_t CLERS_NOID = 0xFFFFFFFFu;
+
+CRT_HD void clers_state_init(ClersState &S, const ClersIO &io) {
+	S.cler = 0; S.vertex_count = 0; S.splitpos = 0;
+	S.cw = io.nclers ? load_u64(io.clers) : 0; S.cw_next = io.nclers > 8 ? load_u64(io.clers + 8) : 0;
+	S.g = 0; S.start = 0; S.end = 0;
+	S.nfront = S.norder = S.cursor = S.ndelayed = 0;
+	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.cv0 = S.cv1 = S.cv2 = S.cprev = S.cnext = 0;
+	S.eflush = S.qflush = S.fflush = S.pflush = 0;
+}
+
+// Runs at most `budget` symbols / FIFO pops.  Returns 1 when all groups are done, 0 when the caller must drain the
+// staging rings and call again (budget exhausted, or a group table that moves the face cursor), < 0 on a topology error.
+template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &S, int budget) {
 	const int splitbits = ilog2_u32(io.nvert) + 1;
-	const uint32_t NONE = 0xFFFFFFFFu;
-#define CRT_NEXT_CLER(c)                                                                              \
-	do {                                                                                              \
-		if(cler >= io.nclers) return -5;                                                              \
-		c = (uint32_t)(cw & 0xffu); cw >>= 8; cler++;                                                 \
-		if((cler & 7u) == 0) { cw = cw_next; cw_next = (cler + 8 < io.nclers) ? load_u64(io.clers + cler + 8) : 0; } \
+	// state in locals for the duration of the run
+	uint32_t cler = S.cler, vcount = S.vertex_count, start = S.start, end = S.end;
+	uint32_t nfront = S.nfront, norder = S.norder, cursor = S.cursor, ndel = S.ndelayed;
+	uint64_t cw = S.cw, cwn = S.cw_next, splitpos = S.splitpos;
+	uint32_t have = S.have, lp = S.lp, ln = S.ln, f = S.cf, v0 = S.cv0, v1 = S.cv1, v2 = S.cv2, prev = S.cprev, next = S.cnext;
+	uint32_t g = S.g, fflush = S.fflush;
+	const uint32_t eflush = S.eflush, qflush = S.qflush, nclers = io.nclers, nvert = io.nvert, cap = io.cap;
+	int rc = 0;
+#define CRT_NEXT_CLER(c)                                                                                  \
+	do {                                                                                                  \
+		if(cler >= nclers) { rc = -5; goto done; }                                                        \
+		c = (uint32_t)cw & 0xffu; cw >>= 8; cler++;                                                       \
+		if((cler & 7u) == 0) { cw = cwn; cwn = (cler + 8 < nclers) ? load_u64(io.clers + cler + 8) : 0; } \
 	} while(0)
-	for(uint32_t g = 0; g < io.ngroups; g++) {
-		uint32_t end = io.group_ends[g]*3;
-		if(end > io.nface*3) end = io.nface*3;
-		uint32_t start = g ? io.group_ends[g - 1]*3 : 0;
-		if(start > io.nface*3) start = io.nface*3;
-		uint32_t nfront = 0, norder = 0, cursor = 0, ndelayed = 0;
-		bool have = false;                 // current edge (the one created last) is held in registers
-		uint32_t cf = 0; EdgeA ce = {0, 0, 0, 0}; EdgeB cl = {0, 0};
-		while(start < end) {
-			if(!have && cursor >= norder && ndelayed == 0) {
-				if(nfront + 3 > io.cap) return -5;
-				uint32_t last = vertex_count - 1;
+#define CRT_SET_NEXT(x, v) do { if((x) >= eflush) rg.stB_next(x, v); else io.eb[x].next = (v); } while(0)
+#define CRT_SET_PREV(x, v) do { if((x) >= eflush) rg.stB_prev(x, v); else io.eb[x].prev = (v); } while(0)
+#define CRT_SET_DEL(x)     do { if((x) >= eflush) rg.stA_del(x); else io.ea[x].deleted = 1; } while(0)
+#define CRT_MATERIALISE()                                                                                 \
+	do {                                                                                                  \
+		if(nfront >= cap) { rc = -5; goto done; }                                                         \
+		f = nfront++;                                                                                     \
+		rg.stA(f, v0, v1, v2, 0); rg.stB(f, prev, next);                                                  \
+		if(lp) CRT_SET_NEXT(prev, f);                                                                     \
+		if(ln) CRT_SET_PREV(next, f);                                                                     \
+		lp = ln = 0;                                                                                      \
+	} while(0)
+	for(;;) {
+		if(!have) {
+			if(start >= end) {                         // open the next group: fresh front (decoder.cpp:173-178, 207-221)
+				if(g >= io.ngroups) { rc = 1; goto done; }
+				uint32_t e = io.group_ends[g];
+				if(e > io.nface) e = io.nface;
+				uint32_t st = g ? io.group_ends[g - 1] : 0;
+				if(st > io.nface) st = io.nface;
+				if(st != start) {                      // malformed group table moves the cursor: drain staged faces first
+					if(fflush != start) { rc = 0; goto done; }
+					fflush = st;
+				}
+				g++;
+				start = st; end = e;
+				nfront = norder = cursor = ndel = 0;
+				// the rings restart with the group; ids below the (stale) flushed limits must not be looked up in global
+				// memory, so ask for a drain, which resets the limits, before touching the new front
+				if(eflush | qflush) { S.eflush = 0; S.qflush = 0; rc = 0; goto done; }
+				continue;
+			}
+			if(budget-- <= 0) { rc = 0; goto done; }
+			if(cursor < norder) { f = (cursor >= qflush) ? rg.ldQ(cursor) : io.order[cursor]; cursor++; }
+			else if(ndel) f = io.delayed[--ndel];
+			else {                                     // nothing pending: start triangle (decoder.cpp:224-259)
+				if(nfront + 3 > cap) { rc = -5; goto done; }
+				uint32_t last = vcount - 1;
 				uint32_t vi[3];
 				uint32_t mask = 0, c;
 				CRT_NEXT_CLER(c);
@@ -411,107 +471,125 @@ CRT_HD int clers_decode_ring(const ClersIO &io, const ClersRing &rg, uint32_t *v
 					uint32_t v;
 					if(mask & (1u << k)) {
 						v = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
-						if(v >= io.nvert) return -5;
+						if(v >= nvert) { rc = -5; goto done; }
 					} else {
-						if(vertex_count >= io.nvert) return -5;
-						clers_put_pred(io, vertex_count, last, last, last);
-						last = v = vertex_count++;
+						if(vcount >= nvert) { rc = -5; goto done; }
+						rg.stP(vcount, last, last, last);
+						last = v = vcount++;
 					}
 					vi[k] = v;
 				}
-				clers_put_face(io, start, vi[0], vi[1], vi[2]);
-				start += 3;
+				rg.stF(start, vi[0], vi[1], vi[2]);
+				start += 1;
 				const uint32_t b = nfront;
-				const EdgeA a0 = {vi[1], vi[2], vi[0], 0}, a1 = {vi[2], vi[0], vi[1], 0}, a2 = {vi[0], vi[1], vi[2], 0};
-				const EdgeB b0 = {b + 2, b + 1}, b1 = {b + 0, b + 2}, b2 = {b + 1, b + 0};
-				io.ea[b] = a0; io.eb[b] = b0; ra[b & RM] = a0; rb[b & RM] = b0;
-				io.ea[b + 1] = a1; io.eb[b + 1] = b1; ra[(b + 1) & RM] = a1; rb[(b + 1) & RM] = b1;
-				io.ea[b + 2] = a2; io.eb[b + 2] = b2; ra[(b + 2) & RM] = a2; rb[(b + 2) & RM] = b2;
-				for(uint32_t k = 0; k < 3; k++) { io.order[norder] = b + k; rq[norder & QM] = b + k; norder++; }
-				nfront += 3;
+				rg.stA(b, vi[1], vi[2], vi[0], 0);     rg.stB(b, b + 2, b + 1);
+				rg.stA(b + 1, vi[2], vi[0], vi[1], 0); rg.stB(b + 1, b + 0, b + 2);
+				rg.stA(b + 2, vi[0], vi[1], vi[2], 0); rg.stB(b + 2, b + 1, b + 0);
+				rg.stQ(norder, b); rg.stQ(norder + 1, b + 1); rg.stQ(norder + 2, b + 2);
+				norder += 3; nfront += 3;
 				continue;
 			}
-			uint32_t f; EdgeA e; EdgeB el;
-			if(have) { f = cf; e = ce; el = cl; have = false; }
-			else {
-				if(cursor < norder) { f = (cursor + Q >= norder) ? rq[cursor & QM] : io.order[cursor]; cursor++; }
-				else f = io.delayed[--ndelayed];
-				const bool inw = f + R >= nfront;
-				e = inw ? ra[f & RM] : io.ea[f];
-				if(e.deleted) continue;
-				el = inw ? rb[f & RM] : io.eb[f];
-			}
+			uint32_t del;
+			if(f >= eflush) rg.ldA(f, v0, v1, v2, del); else { const EdgeA a = io.ea[f]; v0 = a.v0; v1 = a.v1; v2 = a.v2; del = a.deleted; }
+			if(del) continue;
+			if(f >= eflush) rg.ldB(f, prev, next); else { const EdgeB l = io.eb[f]; prev = l.prev; next = l.next; }
+			lp = ln = 0; have = 1;
+		}
+		// ---- strip: the current edge stays in registers from symbol to symbol ----
+		for(;;) {
+			if(budget-- <= 0) { rc = 0; goto done; }
 			uint32_t c;
 			CRT_NEXT_CLER(c);
-			if(c == C_BOUNDARY) continue;
-			if(nfront + 2 > io.cap) return -5;
-			const uint32_t ne = nfront;
-			uint32_t opposite;
-			if(c == C_VERTEX || c == C_SPLIT) {
-				if(c == C_SPLIT) {
-					opposite = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
-					if(opposite >= io.nvert) return -5;
-				} else {
-					if(vertex_count >= io.nvert) return -5;
-					clers_put_pred(io, vertex_count, e.v1, e.v0, e.v2);
-					opposite = vertex_count++;
-				}
-				io.eb[el.prev].next = ne;     if(el.prev + R >= ne) rb[el.prev & RM].next = ne;
-				io.eb[el.next].prev = ne + 1; if(el.next + R >= ne) rb[el.next & RM].prev = ne + 1;
-				const EdgeA a0 = {e.v0, opposite, e.v1, 0}, a1 = {opposite, e.v1, e.v0, 0};
-				const EdgeB b0 = {el.prev, ne + 1}, b1 = {ne, el.next};
-				io.ea[ne] = a0; io.eb[ne] = b0; ra[ne & RM] = a0; rb[ne & RM] = b0;
-				io.ea[ne + 1] = a1; io.eb[ne + 1] = b1; ra[(ne + 1) & RM] = a1; rb[(ne + 1) & RM] = b1;
-				io.order[norder] = ne + 1; rq[norder & QM] = ne + 1; norder++;
-				nfront += 2;
-				cf = ne; ce = a0; cl = b0; have = true;
+			if(c == C_VERTEX) {
+				if(vcount >= nvert || nfront >= cap) { rc = -5; goto done; }
+				rg.stP(vcount, v1, v0, v2);
+				const uint32_t opp = vcount++, b = nfront++;
+				rg.stA(b, opp, v1, v0, 0); rg.stB(b, CLERS_NOID, next);      // second new edge: persistent, queued
+				CRT_SET_PREV(next, b);
+				rg.stQ(norder, b); norder++;
+				rg.stF(start, v1, v0, opp); start++;
+				v2 = v1; v1 = opp; next = b; lp = 1; ln = 1; f = CLERS_NOID;     // first new edge: registers only
 			} else if(c == C_LEFT) {
-				const uint32_t p = el.prev;
-				const bool pw = p + R >= ne;
-				const EdgeB pl = pw ? rb[p & RM] : io.eb[p];
-				opposite = pw ? ra[p & RM].v0 : io.ea[p].v0;
-				io.ea[p].deleted = 1;         if(pw) ra[p & RM].deleted = 1;
-				io.eb[pl.prev].next = ne;     if(pl.prev + R >= ne) rb[pl.prev & RM].next = ne;
-				io.eb[el.next].prev = ne;     if(el.next + R >= ne) rb[el.next & RM].prev = ne;
-				const EdgeA a0 = {opposite, e.v1, e.v0, 0};
-				const EdgeB b0 = {pl.prev, el.next};
-				io.ea[ne] = a0; io.eb[ne] = b0; ra[ne & RM] = a0; rb[ne & RM] = b0;
-				nfront += 1;
-				cf = ne; ce = a0; cl = b0; have = true;
+				if((lp | ln) && prev == next) CRT_MATERIALISE();                 // 2-edge loop: deferred fields would be read
+				uint32_t pp, pn, pv0, t1, t2, t3;
+				if(prev >= eflush) { rg.ldB(prev, pp, pn); rg.ldA(prev, pv0, t1, t2, t3); }
+				else { const EdgeB l = io.eb[prev]; pp = l.prev; pn = l.next; pv0 = io.ea[prev].v0; t1 = t2 = t3 = 0; }
+				(void)pn; (void)t1; (void)t2; (void)t3;
+				CRT_SET_DEL(prev);
+				rg.stF(start, v1, v0, pv0); start++;
+				v2 = v0; v0 = pv0; prev = pp; lp = 1; ln = 1; f = CLERS_NOID;
 			} else if(c == C_RIGHT) {
-				const uint32_t n = el.next;
-				const bool nw = n + R >= ne;
-				const EdgeB nl = nw ? rb[n & RM] : io.eb[n];
-				opposite = nw ? ra[n & RM].v1 : io.ea[n].v1;
-				io.ea[n].deleted = 1;         if(nw) ra[n & RM].deleted = 1;
-				io.eb[nl.next].prev = ne;     if(nl.next + R >= ne) rb[nl.next & RM].prev = ne;
-				io.eb[el.prev].next = ne;     if(el.prev + R >= ne) rb[el.prev & RM].next = ne;
-				const EdgeA a0 = {e.v0, opposite, e.v1, 0};
-				const EdgeB b0 = {el.prev, nl.next};
-				io.ea[ne] = a0; io.eb[ne] = b0; ra[ne & RM] = a0; rb[ne & RM] = b0;
-				nfront += 1;
-				cf = ne; ce = a0; cl = b0; have = true;
+				if((lp | ln) && prev == next) CRT_MATERIALISE();
+				uint32_t np, nn, nv1, t0, t2, t3;
+				if(next >= eflush) { rg.ldB(next, np, nn); rg.ldA(next, t0, nv1, t2, t3); }
+				else { const EdgeB l = io.eb[next]; np = l.prev; nn = l.next; nv1 = io.ea[next].v1; t0 = t2 = t3 = 0; }
+				(void)np; (void)t0; (void)t2; (void)t3;
+				CRT_SET_DEL(next);
+				rg.stF(start, v1, v0, nv1); start++;
+				v2 = v1; v1 = nv1; next = nn; lp = 1; ln = 1; f = CLERS_NOID;
+			} else if(c == C_BOUNDARY) {
+				if(f == CLERS_NOID) CRT_MATERIALISE();
+				have = 0; break;
 			} else if(c == C_DELAY) {
-				io.delayed[ndelayed++] = f;
-				continue;
+				if(f == CLERS_NOID) CRT_MATERIALISE();
+				io.delayed[ndel++] = f;
+				have = 0; break;
 			} else if(c == C_END) {
-				const uint32_t p = el.prev, n = el.next;
-				const bool pw = p + R >= ne, nw = n + R >= ne;
-				const EdgeB pl = pw ? rb[p & RM] : io.eb[p];
-				const EdgeB nl = nw ? rb[n & RM] : io.eb[n];
-				opposite = pw ? ra[p & RM].v0 : io.ea[p].v0;
-				io.ea[p].deleted = 1;         if(pw) ra[p & RM].deleted = 1;
-				io.ea[n].deleted = 1;         if(nw) ra[n & RM].deleted = 1;
-				io.eb[pl.prev].next = nl.next; if(pl.prev + R >= ne) rb[pl.prev & RM].next = nl.next;
-				io.eb[nl.next].prev = pl.prev; if(nl.next + R >= ne) rb[nl.next & RM].prev = pl.prev;
-			} else return -5;
-			clers_put_face(io, start, e.v1, e.v0, opposite);
-			start += 3;
+				if((lp | ln) && prev == next) CRT_MATERIALISE();
+				uint32_t pp, pn, np, nn, pv0, t1, t2, t3;
+				if(prev >= eflush) { rg.ldB(prev, pp, pn); rg.ldA(prev, pv0, t1, t2, t3); }
+				else { const EdgeB l = io.eb[prev]; pp = l.prev; pn = l.next; pv0 = io.ea[prev].v0; t1 = t2 = t3 = 0; }
+				if(next >= eflush) rg.ldB(next, np, nn); else { const EdgeB l = io.eb[next]; np = l.prev; nn = l.next; }
+				(void)pn; (void)np; (void)t1; (void)t2; (void)t3;
+				CRT_SET_DEL(prev);
+				CRT_SET_DEL(next);
+				CRT_SET_NEXT(pp, nn);
+				CRT_SET_PREV(nn, pp);
+				rg.stF(start, v1, v0, pv0); start++;
+				have = 0; break;
+			} else if(c == C_SPLIT) {
+				if(nfront >= cap) { rc = -5; goto done; }
+				const uint32_t opp = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+				if(opp >= nvert) { rc = -5; goto done; }
+				const uint32_t b = nfront++;
+				rg.stA(b, opp, v1, v0, 0); rg.stB(b, CLERS_NOID, next);
+				CRT_SET_PREV(next, b);
+				rg.stQ(norder, b); norder++;
+				rg.stF(start, v1, v0, opp); start++;
+				v2 = v1; v1 = opp; next = b; lp = 1; ln = 1; f = CLERS_NOID;
+			} else { rc = -5; goto done; }
+			if(start >= end) { have = 0; break; }      // group complete: the front is discarded (decoder.cpp:223)
 		}
 	}
+done:
+	S.cler = cler; S.vertex_count = vcount; S.start = start; S.end = end;
+	S.nfront = nfront; S.norder = norder; S.cursor = cursor; S.ndelayed = ndel;
+	S.cw = cw; S.cw_next = cwn; S.splitpos = splitpos;
+	S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.cv0 = v0; S.cv1 = v1; S.cv2 = v2; S.cprev = prev; S.cnext = next;
+	S.g = g; S.fflush = fflush;
+	return rc;
 #undef CRT_NEXT_CLER
-	*vertex_count_out = vertex_count;
-	return 0;
+#undef CRT_SET_NEXT
+#undef CRT_SET_PREV
+#undef CRT_SET_DEL
+#undef CRT_MATERIALISE
 }
+
+// Plain-array ring policy (tests/host_emul; the kernel has its own shared-memory policy with the same interface).
+struct ArrayRings {
+	uint4_t *ra; uint2_t *rb; uint32_t *rq; uint4_t *sf; uint4_t *sp;
+	uint32_t RM, QM, FM, PM;
+	CRT_HD void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const { const uint4_t v = ra[id & RM]; a = v.x; b = v.y; c = v.z; d = v.w; }
+	CRT_HD void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { ra[id & RM] = uint4_t{a, b, c, d}; }
+	CRT_HD void stA_del(uint32_t id) { ra[id & RM].w = 1; }
+	CRT_HD void ldB(uint32_t id, uint32_t &p, uint32_t &n) const { const uint2_t v = rb[id & RM]; p = v.x; n = v.y; }
+	CRT_HD void stB(uint32_t id, uint32_t p, uint32_t n) { rb[id & RM] = uint2_t{p, n}; }
+	CRT_HD void stB_prev(uint32_t id, uint32_t p) { rb[id & RM].x = p; }
+	CRT_HD void stB_next(uint32_t id, uint32_t n) { rb[id & RM].y = n; }
+	CRT_HD uint32_t ldQ(uint32_t i) const { return rq[i & QM]; }
+	CRT_HD void stQ(uint32_t i, uint32_t v) { rq[i & QM] = v; }
+	CRT_HD void stF(uint32_t face, uint32_t a, uint32_t b, uint32_t c) { sf[face & FM] = uint4_t{a, b, c, 0}; }
+	CRT_HD void stP(uint32_t v, uint32_t a, uint32_t b, uint32_t c) { sp[v & PM] = uint4_t{a, b, c, 0}; }
+};
 
 }  // namespace crtb

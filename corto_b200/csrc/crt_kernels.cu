@@ -270,15 +270,56 @@ __global__ void __launch_bounds__(256) k_bit_unpack(DevBatch B, const Tile *tile
 }
 
 // =========================================================================================================
-// K4  CLERS automaton: one warp per mesh, lane 0 runs the serial machine.  The hot part of its state (last R front
-//     edges, last Q FIFO entries) is cached in shared memory rings, global memory is the write-through backing store.
-//     The automaton is latency-bound (a dependent pointer chase per symbol), so the design goal is the shortest
-//     dependent chain per symbol, not bandwidth: see clers_decode_ring in crt_device.cuh.
+// K4  CLERS automaton: one warp per mesh.  Lane 0 runs the serial machine (clers_run, crt_device.cuh) against
+//     shared-memory rings; every CLERS_BUDGET symbols ALL lanes drain the staged faces / predictions to global memory
+//     with coalesced stores and write ring entries leaving the window back to the reach-back store.  The machine is
+//     instruction-latency bound (ncu: CPI 4.4, one warp per SM sub-partition), so the design goal is the smallest
+//     number of dependent instructions per symbol, not bandwidth.
 // =========================================================================================================
+extern __shared__ __align__(16) uint8_t crt_smem[];
+
+// Shared-memory ring policy for clers_run: explicit 32-bit shared-space addressing (ld/st.shared), bases precomputed
+// once, so a ring access is mask + shift-add + LDS/STS.
+struct SmemRings {
+	uint32_t aA, aB, aQ, aF, aP;      // shared-space byte addresses of the rings
+	uint32_t RM, QM, FM, PM;
+	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const {
+		asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & RM) << 4)));
+	}
+	__device__ __forceinline__ void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aA + ((id & RM) << 4)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+	}
+	__device__ __forceinline__ void stA_del(uint32_t id) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aA + ((id & RM) << 4) + 12u), "r"(1u) : "memory"); }
+	__device__ __forceinline__ void ldB(uint32_t id, uint32_t &p, uint32_t &n) const {
+		asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(p), "=r"(n) : "r"(aB + ((id & RM) << 3)));
+	}
+	__device__ __forceinline__ void stB(uint32_t id, uint32_t p, uint32_t n) {
+		asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(aB + ((id & RM) << 3)), "r"(p), "r"(n) : "memory");
+	}
+	__device__ __forceinline__ void stB_prev(uint32_t id, uint32_t p) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3)), "r"(p) : "memory"); }
+	__device__ __forceinline__ void stB_next(uint32_t id, uint32_t n) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3) + 4u), "r"(n) : "memory"); }
+	__device__ __forceinline__ uint32_t ldQ(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aQ + ((i & QM) << 2))); return v; }
+	__device__ __forceinline__ void stQ(uint32_t i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aQ + ((i & QM) << 2)), "r"(v) : "memory"); }
+	__device__ __forceinline__ void stF(uint32_t face, uint32_t a, uint32_t b, uint32_t c) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aF + ((face & FM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
+	}
+	__device__ __forceinline__ void stP(uint32_t v, uint32_t a, uint32_t b, uint32_t c) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aP + ((v & PM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
+	}
+};
+
+constexpr int CLERS_BUDGET = 80;       // symbols between drains; staging rings hold >= 3*budget entries
+constexpr uint32_t CLERS_STAGE = 256;  // faces / predictions staged (power of two >= 3*CLERS_BUDGET)
+
 __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
                                               uint32_t R, uint32_t Q) {
-	extern __shared__ __align__(16) uint8_t smem_raw[];
-	const int lane = threadIdx.x;
+	const uint32_t lane = threadIdx.x;
+	SmemRings rg;
+	const uint32_t oA = 0, oB = R*16u, oQ = oB + R*8u, oF = oQ + Q*4u, oP = oF + CLERS_STAGE*16u;
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(crt_smem);
+	rg.aA = sbase + oA; rg.aB = sbase + oB; rg.aQ = sbase + oQ; rg.aF = sbase + oF; rg.aP = sbase + oP;
+	rg.RM = R - 1; rg.QM = Q - 1; rg.FM = CLERS_STAGE - 1; rg.PM = CLERS_STAGE - 1;
+	const uint32_t W = R - 3u*CLERS_BUDGET, QW = Q - 3u*CLERS_BUDGET;
 	for(;;) {
 		uint32_t w = 0;
 		if(lane == 0) w = atomicAdd(ticket, 1u);
@@ -286,38 +327,66 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 		if(w >= nwork) break;
 		const uint32_t mi = mesh_order[w];
 		const MeshDesc *M = B.mesh + mi;
-		uint32_t vcount = 0;
+		const TunDesc td = B.tun[M->clers_tun];
+		ClersIO io;
+		io.clers = B.symbols + td.out_off; io.nclers = td.size;
+		io.split = (const uint32_t *)(B.blobs + M->split_off); io.split_nwords = M->split_nwords;
+		io.group_ends = B.group_ends + M->group0; io.ngroups = M->ngroups;
+		io.nvert = M->nvert; io.nface = M->nface;
+		const size_t slot = blockIdx.x;
+		io.cap = scratch.cap;
+		io.ea = scratch.ea + slot*scratch.cap; io.eb = scratch.eb + slot*scratch.cap;
+		io.order = scratch.order + slot*scratch.cap; io.delayed = scratch.delayed + slot*scratch.cap;
+		const uint32_t need = 3u*M->max_group_faces + 3u;
+		if(need < io.cap) io.cap = need;
+		io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
+		io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
+		io.pred = (uint32_t *)M->pred_ptr;
+		ClersState S;
+		clers_state_init(S, io);
 		int rc = 0;
-		if(lane == 0) {
-			const TunDesc td = B.tun[M->clers_tun];
-			ClersIO io;
-			io.clers = B.symbols + td.out_off; io.nclers = td.size;
-			io.split = (const uint32_t *)(B.blobs + M->split_off); io.split_nwords = M->split_nwords;
-			io.group_ends = B.group_ends + M->group0; io.ngroups = M->ngroups;
-			io.nvert = M->nvert; io.nface = M->nface;
-			const size_t slot = blockIdx.x;
-			io.cap = scratch.cap;
-			io.ea = scratch.ea + slot*scratch.cap; io.eb = scratch.eb + slot*scratch.cap;
-			io.order = scratch.order + slot*scratch.cap; io.delayed = scratch.delayed + slot*scratch.cap;
-			uint32_t need = 3u*M->max_group_faces + 3u;
-			if(need < io.cap) io.cap = need;
-			io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
-			io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
-			io.pred = (uint32_t *)M->pred_ptr;
-			ClersRing rg;
-			rg.R = R; rg.Q = Q;
-			rg.ra = (EdgeA *)smem_raw;
-			rg.rb = (EdgeB *)(smem_raw + (size_t)R*sizeof(EdgeA));
-			rg.rq = (uint32_t *)(smem_raw + (size_t)R*(sizeof(EdgeA) + sizeof(EdgeB)));
-			rc = clers_decode_ring(io, rg, &vcount);
-			if(rc) B.status[mi] = rc;
-			B.vertex_count[mi] = vcount;
+		for(;;) {
+			if(lane == 0) rc = clers_run(io, rg, S, CLERS_BUDGET);
+			rc = __shfl_sync(0xffffffffu, rc, 0);
+			// ---- cooperative drain (all lanes) ----
+			const uint32_t f0 = __shfl_sync(0xffffffffu, S.fflush, 0), f1 = __shfl_sync(0xffffffffu, S.start, 0);
+			const uint32_t p0 = __shfl_sync(0xffffffffu, S.pflush, 0), p1 = __shfl_sync(0xffffffffu, S.vertex_count, 0);
+			const uint32_t e0 = __shfl_sync(0xffffffffu, S.eflush, 0), nf = __shfl_sync(0xffffffffu, S.nfront, 0);
+			const uint32_t q0 = __shfl_sync(0xffffffffu, S.qflush, 0), no = __shfl_sync(0xffffffffu, S.norder, 0), cu = __shfl_sync(0xffffffffu, S.cursor, 0);
+			__syncwarp();
+			{   // faces: 3 index words per face, consecutive lanes write consecutive words
+				const uint32_t nw = (f1 - f0)*3u;
+				const uint4 *sf = (const uint4 *)(crt_smem + oF);
+				for(uint32_t k = lane; k < nw; k += 32) {
+					const uint32_t face = f0 + k/3u, comp = k - (k/3u)*3u;
+					const uint32_t v = ((const uint32_t *)(sf + (face & rg.FM)))[comp];
+					const size_t at = (size_t)f0*3u + k;
+					if(io.faces16) io.faces16[at] = (uint16_t)v; else io.faces32[at] = v;
+				}
+			}
+			{   // predictions
+				const uint4 *sp = (const uint4 *)(crt_smem + oP);
+				uint4 *dst = (uint4 *)io.pred;
+				for(uint32_t v = p0 + lane; v < p1; v += 32) dst[v] = sp[v & rg.PM];
+			}
+			const uint32_t e1 = nf > W ? nf - W : 0u;
+			if(e1 > e0) {   // ring entries leaving the window -> reach-back store
+				for(uint32_t id = e0 + lane; id < e1; id += 32) {
+					const uint4 a = ((const uint4 *)(crt_smem + oA))[id & rg.RM]; const uint2 l = ((const uint2 *)(crt_smem + oB))[id & rg.RM];
+					io.ea[id] = EdgeA{a.x, a.y, a.z, a.w}; io.eb[id] = EdgeB{l.x, l.y};
+				}
+			}
+			const uint32_t q1 = no > QW ? no - QW : 0u;
+			if(q1 > q0) for(uint32_t i = max(q0, cu) + lane; i < q1; i += 32) io.order[i] = rg.ldQ(i);
+			__syncwarp();
+			if(lane == 0) { S.fflush = f1; S.pflush = p1; if(e1 > e0) S.eflush = e1; if(q1 > q0) S.qflush = q1; }
+			if(rc != 0) break;
 		}
-		vcount = __shfl_sync(0xffffffffu, vcount, 0);
-		rc = __shfl_sync(0xffffffffu, rc, 0);
+		uint32_t vcount = __shfl_sync(0xffffffffu, S.vertex_count, 0);
+		if(lane == 0) { if(rc < 0) B.status[mi] = rc; B.vertex_count[mi] = vcount; }
 		// vertices the stream never created (corrupt / truncated input): neutral prediction so later passes stay in bounds
 		uint4 *pred = (uint4 *)M->pred_ptr;
-		if(rc) vcount = 0;
+		if(rc < 0) vcount = 0;
 		for(uint32_t v = vcount + lane; v < M->nvert; v += 32) pred[v] = make_uint4(0, 0, 0, 0);
 		__syncwarp();
 	}
@@ -640,10 +709,10 @@ int launch_bit_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 }
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
-	// few meshes: big rings (2 CTAs per SM);  many meshes: smaller rings so that more serial chains share an SM
+	// few meshes: bigger rings (3 CTAs per SM);  many meshes: smaller rings so that more serial chains share an SM
 	uint32_t R = 4096, Q = 2048;
 	if(nwork > (uint32_t)sms*2u) { R = 1024; Q = 1024; }
-	const size_t smem = (size_t)R*(sizeof(EdgeA) + sizeof(EdgeB)) + (size_t)Q*4;
+	const size_t smem = (size_t)R*24 + (size_t)Q*4 + 2*(size_t)CLERS_STAGE*16;
 	static size_t configured = 0;
 	if(configured < smem) {
 		cudaError_t e = cudaFuncSetAttribute(k_clers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

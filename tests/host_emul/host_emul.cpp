@@ -6,6 +6,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include "../../corto_b200/csrc/crt_device.cuh"
 #include "../../corto_b200/csrc/crt_walk.h"
 #include "../../include/corto_b200.h"
@@ -59,11 +60,29 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 	uint32_t vc = 0;
 	int rc;
 	if(ring_r == 0) rc = clers_decode_seq(io, &vc);
-	else {
-		std::vector<EdgeA> ra(ring_r); std::vector<EdgeB> rb(ring_r); std::vector<uint32_t> rq(ring_q);
-		ClersRing rg{ra.data(), rb.data(), rq.data(), (uint32_t)ring_r, (uint32_t)ring_q};
-		rc = clers_decode_ring(io, rg, &vc);
-	}
+	else if(ring_r < 0) {
+		// v3 machine (clers_run) with the kernel's drain protocol emulated serially; R = -ring_r, Q = ring_q, budget = R/8
+		const uint32_t R = (uint32_t)(-ring_r), Q = (uint32_t)ring_q;
+		const int budget = (int)(std::min(R, Q)/8);
+		uint32_t ST = 1; while(ST < 3u*budget) ST <<= 1;
+		std::vector<uint4_t> ra(R), sf(ST), sp(ST); std::vector<uint2_t> rb(R); std::vector<uint32_t> rq(Q);
+		ArrayRings rg{ra.data(), rb.data(), rq.data(), sf.data(), sp.data(), R - 1, Q - 1, ST - 1, ST - 1};
+		const uint32_t W = R - 3u*budget, QW = Q - 3u*budget;
+		ClersState S; clers_state_init(S, io);
+		for(int guard = 0; guard < (1 << 30); guard++) {
+			rc = clers_run(io, rg, S, budget);
+			for(uint32_t f = S.fflush; f < S.start; f++) { const uint4_t v = sf[f & (ST - 1)]; faces[(size_t)f*3] = v.x; faces[(size_t)f*3 + 1] = v.y; faces[(size_t)f*3 + 2] = v.z; }
+			for(uint32_t v = S.pflush; v < S.vertex_count; v++) { const uint4_t x = sp[v & (ST - 1)]; pred[(size_t)v*4] = x.x; pred[(size_t)v*4 + 1] = x.y; pred[(size_t)v*4 + 2] = x.z; pred[(size_t)v*4 + 3] = 0; }
+			S.fflush = S.start; S.pflush = S.vertex_count;
+			const uint32_t e1 = S.nfront > W ? S.nfront - W : 0;
+			if(e1 > S.eflush) { for(uint32_t id = S.eflush; id < e1; id++) { const uint4_t a = ra[id & (R - 1)]; const uint2_t l = rb[id & (R - 1)]; ea[id] = EdgeA{a.x, a.y, a.z, a.w}; eb[id] = EdgeB{l.x, l.y}; } S.eflush = e1; }
+			const uint32_t q1 = S.norder > QW ? S.norder - QW : 0;
+			if(q1 > S.qflush) { for(uint32_t i = std::max(S.qflush, S.cursor); i < q1; i++) order[i] = rq[i & (Q - 1)]; S.qflush = q1; }
+			if(rc != 0) break;
+		}
+		vc = S.vertex_count;
+		rc = rc < 0 ? rc : 0;
+	} else rc = -99;
 	for(uint32_t v = 0; v < pm.nvert; v++) for(int k = 0; k < 3; k++) prediction[v*3 + k] = pred[(size_t)v*4 + k];
 	return rc;
 }
