@@ -407,73 +407,105 @@ CRT_HD void clers_state_init(ClersState &S, const ClersIO &io) {
 	S.eflush = S.qflush = S.fflush = S.pflush = 0;
 }
 
-// Runs at most `budget` symbols / FIFO pops.  Returns 1 when all groups are done, 0 when the caller must drain the
-// staging rings and call again (budget exhausted, or a group table that moves the face cursor), < 0 on a topology error.
-template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &S, int budget) {
-	const int splitbits = ilog2_u32(io.nvert) + 1;
-	// state in locals for the duration of the run
+// Slow paths kept out of line so the hot loop stays small (reach-back into global memory is rare by construction).
+#ifdef __CUDACC__
+#define CRT_COLD __device__ __host__ __noinline__
+#else
+#define CRT_COLD __attribute__((noinline))
+#endif
+struct EdgeRec { uint32_t v0, v1, v2, del, p, n; };
+CRT_COLD static void clers_g_set_next(EdgeB *eb, uint32_t x, uint32_t v) { eb[x].next = v; }
+CRT_COLD static void clers_g_set_prev(EdgeB *eb, uint32_t x, uint32_t v) { eb[x].prev = v; }
+CRT_COLD static void clers_g_set_del(EdgeA *ea, uint32_t x) { ea[x].deleted = 1; }
+CRT_COLD static EdgeRec clers_g_load(const EdgeA *ea, const EdgeB *eb, uint32_t x) {   // by value: nothing of the hot loop gets its address taken
+	const EdgeA a = ea[x]; const EdgeB l = eb[x];
+	EdgeRec r; r.v0 = a.v0; r.v1 = a.v1; r.v2 = a.v2; r.del = a.deleted; r.p = l.prev; r.n = l.next;
+	return r;
+}
+
+// Runs at most `budget` symbols.  Returns 1 when all groups are done, 0 when the caller must drain the staging rings
+// and call again (budget exhausted, or a group table that moves the face cursor), < 0 on a topology error (the state is
+// then meaningless).  `splitbits` = ilog2(nvert)+1 (decoder.cpp:219), passed in so it is computed once per mesh.
+template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &S, int budget, int splitbits) {
 	uint32_t cler = S.cler, vcount = S.vertex_count, start = S.start, end = S.end;
 	uint32_t nfront = S.nfront, norder = S.norder, cursor = S.cursor, ndel = S.ndelayed;
 	uint64_t cw = S.cw, cwn = S.cw_next, splitpos = S.splitpos;
 	uint32_t have = S.have, lp = S.lp, ln = S.ln, f = S.cf, v0 = S.cv0, v1 = S.cv1, v2 = S.cv2, prev = S.cprev, next = S.cnext;
 	uint32_t g = S.g, fflush = S.fflush;
 	const uint32_t eflush = S.eflush, qflush = S.qflush, nclers = io.nclers, nvert = io.nvert, cap = io.cap;
+	// symbols this run may consume: the budget, or what is left of the stream (running dry with faces missing = error)
+	uint32_t n = nclers - cler;
+	if(n > (uint32_t)budget) n = (uint32_t)budget;
 	int rc = 0;
-#define CRT_NEXT_CLER(c)                                                                                  \
-	do {                                                                                                  \
-		if(cler >= nclers) { rc = -5; goto done; }                                                        \
-		c = (uint32_t)cw & 0xffu; cw >>= 8; cler++;                                                       \
+#define CRT_FETCH(c)                                                                                     \
+	do {                                                                                                 \
+		c = (uint32_t)cw & 0xffu; cw >>= 8; cler++;                                                      \
 		if((cler & 7u) == 0) { cw = cwn; cwn = (cler + 8 < nclers) ? load_u64(io.clers + cler + 8) : 0; } \
 	} while(0)
-#define CRT_SET_NEXT(x, v) do { if((x) >= eflush) rg.stB_next(x, v); else io.eb[x].next = (v); } while(0)
-#define CRT_SET_PREV(x, v) do { if((x) >= eflush) rg.stB_prev(x, v); else io.eb[x].prev = (v); } while(0)
-#define CRT_SET_DEL(x)     do { if((x) >= eflush) rg.stA_del(x); else io.ea[x].deleted = 1; } while(0)
-#define CRT_MATERIALISE()                                                                                 \
-	do {                                                                                                  \
-		if(nfront >= cap) { rc = -5; goto done; }                                                         \
-		f = nfront++;                                                                                     \
-		rg.stA(f, v0, v1, v2, 0); rg.stB(f, prev, next);                                                  \
-		if(lp) CRT_SET_NEXT(prev, f);                                                                     \
-		if(ln) CRT_SET_PREV(next, f);                                                                     \
-		lp = ln = 0;                                                                                      \
+#define CRT_SET_NEXT(x, v) do { if((x) >= eflush) rg.stB_next(x, v); else clers_g_set_next(io.eb, x, v); } while(0)
+#define CRT_SET_PREV(x, v) do { if((x) >= eflush) rg.stB_prev(x, v); else clers_g_set_prev(io.eb, x, v); } while(0)
+#define CRT_SET_DEL(x)     do { if((x) >= eflush) rg.stA_del(x); else clers_g_set_del(io.ea, x); } while(0)
+#define CRT_MATERIALISE()                                                                                \
+	do {                                                                                                 \
+		if(nfront >= cap) return -5;                                                                     \
+		f = nfront++;                                                                                    \
+		rg.stA(f, v0, v1, v2, 0); rg.stB(f, prev, next);                                                 \
+		if(lp) CRT_SET_NEXT(prev, f);                                                                    \
+		if(ln) CRT_SET_PREV(next, f);                                                                    \
+		lp = ln = 0;                                                                                     \
 	} while(0)
 	for(;;) {
 		if(!have) {
 			if(start >= end) {                         // open the next group: fresh front (decoder.cpp:173-178, 207-221)
-				if(g >= io.ngroups) { rc = 1; goto done; }
+				if(g >= io.ngroups) { rc = 1; break; }
 				uint32_t e = io.group_ends[g];
 				if(e > io.nface) e = io.nface;
 				uint32_t st = g ? io.group_ends[g - 1] : 0;
 				if(st > io.nface) st = io.nface;
 				if(st != start) {                      // malformed group table moves the cursor: drain staged faces first
-					if(fflush != start) { rc = 0; goto done; }
+					if(fflush != start) { rc = 0; break; }
 					fflush = st;
 				}
 				g++;
 				start = st; end = e;
 				nfront = norder = cursor = ndel = 0;
-				// the rings restart with the group; ids below the (stale) flushed limits must not be looked up in global
-				// memory, so ask for a drain, which resets the limits, before touching the new front
-				if(eflush | qflush) { S.eflush = 0; S.qflush = 0; rc = 0; goto done; }
+				// the rings restart with the group: the flushed limits of the old front must go before any id of the new
+				// front is looked up, so hand back to the caller (its drain resets them) and resume
+				if(eflush | qflush) { S.eflush = 0; S.qflush = 0; rc = 0; break; }
 				continue;
 			}
-			if(budget-- <= 0) { rc = 0; goto done; }
-			if(cursor < norder) { f = (cursor >= qflush) ? rg.ldQ(cursor) : io.order[cursor]; cursor++; }
-			else if(ndel) f = io.delayed[--ndel];
+			// next edge: FIFO (skipping edges deleted since they were queued, decoder.cpp:278-279), then the delayed stack
+			uint32_t del = 1;
+			while(cursor < norder) {
+				f = (cursor >= qflush) ? rg.ldQ(cursor) : io.order[cursor];
+				cursor++;
+				if(f >= eflush) { rg.ldA(f, v0, v1, v2, del); if(!del) rg.ldB(f, prev, next); }
+				else { const EdgeRec r = clers_g_load(io.ea, io.eb, f); v0 = r.v0; v1 = r.v1; v2 = r.v2; del = r.del; prev = r.p; next = r.n; }
+				if(!del) break;
+			}
+			if(del && ndel) {
+				f = io.delayed[--ndel];
+				if(f >= eflush) { rg.ldA(f, v0, v1, v2, del); if(!del) rg.ldB(f, prev, next); }
+				else { const EdgeRec r = clers_g_load(io.ea, io.eb, f); v0 = r.v0; v1 = r.v1; v2 = r.v2; del = r.del; prev = r.p; next = r.n; }
+				if(del) continue;
+			}
+			if(!del) { lp = ln = 0; have = 1; }
 			else {                                     // nothing pending: start triangle (decoder.cpp:224-259)
-				if(nfront + 3 > cap) { rc = -5; goto done; }
+				if(n == 0) { rc = (cler >= nclers) ? -5 : 0; break; }
+				n--;
+				if(nfront + 3 > cap) return -5;
 				uint32_t last = vcount - 1;
 				uint32_t vi[3];
 				uint32_t mask = 0, c;
-				CRT_NEXT_CLER(c);
+				CRT_FETCH(c);
 				if(c == C_SPLIT) { mask = getbits(io.split, io.split_nwords, splitpos, 3); splitpos += 3; }
 				for(int k = 0; k < 3; k++) {
 					uint32_t v;
 					if(mask & (1u << k)) {
 						v = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
-						if(v >= nvert) { rc = -5; goto done; }
+						if(v >= nvert) return -5;
 					} else {
-						if(vcount >= nvert) { rc = -5; goto done; }
+						if(vcount >= nvert) return -5;
 						rg.stP(vcount, last, last, last);
 						last = v = vcount++;
 					}
@@ -489,19 +521,15 @@ template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &
 				norder += 3; nfront += 3;
 				continue;
 			}
-			uint32_t del;
-			if(f >= eflush) rg.ldA(f, v0, v1, v2, del); else { const EdgeA a = io.ea[f]; v0 = a.v0; v1 = a.v1; v2 = a.v2; del = a.deleted; }
-			if(del) continue;
-			if(f >= eflush) rg.ldB(f, prev, next); else { const EdgeB l = io.eb[f]; prev = l.prev; next = l.next; }
-			lp = ln = 0; have = 1;
 		}
 		// ---- strip: the current edge stays in registers from symbol to symbol ----
-		for(;;) {
-			if(budget-- <= 0) { rc = 0; goto done; }
+		do {
+			if(n == 0) { rc = (cler >= nclers) ? -5 : 0; goto save; }
+			n--;
 			uint32_t c;
-			CRT_NEXT_CLER(c);
+			CRT_FETCH(c);
 			if(c == C_VERTEX) {
-				if(vcount >= nvert || nfront >= cap) { rc = -5; goto done; }
+				if(vcount >= nvert || nfront >= cap) return -5;
 				rg.stP(vcount, v1, v0, v2);
 				const uint32_t opp = vcount++, b = nfront++;
 				rg.stA(b, opp, v1, v0, 0); rg.stB(b, CLERS_NOID, next);      // second new edge: persistent, queued
@@ -513,7 +541,7 @@ template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &
 				if((lp | ln) && prev == next) CRT_MATERIALISE();                 // 2-edge loop: deferred fields would be read
 				uint32_t pp, pn, pv0, t1, t2, t3;
 				if(prev >= eflush) { rg.ldB(prev, pp, pn); rg.ldA(prev, pv0, t1, t2, t3); }
-				else { const EdgeB l = io.eb[prev]; pp = l.prev; pn = l.next; pv0 = io.ea[prev].v0; t1 = t2 = t3 = 0; }
+				else { const EdgeRec r = clers_g_load(io.ea, io.eb, prev); pv0 = r.v0; pp = r.p; }
 				(void)pn; (void)t1; (void)t2; (void)t3;
 				CRT_SET_DEL(prev);
 				rg.stF(start, v1, v0, pv0); start++;
@@ -522,7 +550,7 @@ template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &
 				if((lp | ln) && prev == next) CRT_MATERIALISE();
 				uint32_t np, nn, nv1, t0, t2, t3;
 				if(next >= eflush) { rg.ldB(next, np, nn); rg.ldA(next, t0, nv1, t2, t3); }
-				else { const EdgeB l = io.eb[next]; np = l.prev; nn = l.next; nv1 = io.ea[next].v1; t0 = t2 = t3 = 0; }
+				else { const EdgeRec r = clers_g_load(io.ea, io.eb, next); nv1 = r.v1; nn = r.n; }
 				(void)np; (void)t0; (void)t2; (void)t3;
 				CRT_SET_DEL(next);
 				rg.stF(start, v1, v0, nv1); start++;
@@ -538,8 +566,8 @@ template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &
 				if((lp | ln) && prev == next) CRT_MATERIALISE();
 				uint32_t pp, pn, np, nn, pv0, t1, t2, t3;
 				if(prev >= eflush) { rg.ldB(prev, pp, pn); rg.ldA(prev, pv0, t1, t2, t3); }
-				else { const EdgeB l = io.eb[prev]; pp = l.prev; pn = l.next; pv0 = io.ea[prev].v0; t1 = t2 = t3 = 0; }
-				if(next >= eflush) rg.ldB(next, np, nn); else { const EdgeB l = io.eb[next]; np = l.prev; nn = l.next; }
+				else { const EdgeRec r = clers_g_load(io.ea, io.eb, prev); pv0 = r.v0; pp = r.p; }
+				if(next >= eflush) rg.ldB(next, np, nn); else { const EdgeRec r = clers_g_load(io.ea, io.eb, next); nn = r.n; }
 				(void)pn; (void)np; (void)t1; (void)t2; (void)t3;
 				CRT_SET_DEL(prev);
 				CRT_SET_DEL(next);
@@ -548,27 +576,27 @@ template <class RG> CRT_HD int clers_run(const ClersIO &io, RG &rg, ClersState &
 				rg.stF(start, v1, v0, pv0); start++;
 				have = 0; break;
 			} else if(c == C_SPLIT) {
-				if(nfront >= cap) { rc = -5; goto done; }
+				if(nfront >= cap) return -5;
 				const uint32_t opp = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
-				if(opp >= nvert) { rc = -5; goto done; }
+				if(opp >= nvert) return -5;
 				const uint32_t b = nfront++;
 				rg.stA(b, opp, v1, v0, 0); rg.stB(b, CLERS_NOID, next);
 				CRT_SET_PREV(next, b);
 				rg.stQ(norder, b); norder++;
 				rg.stF(start, v1, v0, opp); start++;
 				v2 = v1; v1 = opp; next = b; lp = 1; ln = 1; f = CLERS_NOID;
-			} else { rc = -5; goto done; }
-			if(start >= end) { have = 0; break; }      // group complete: the front is discarded (decoder.cpp:223)
-		}
+			} else return -5;
+		} while(start < end);
+		have = 0;                                          // strip over (terminator) or group complete (front discarded, decoder.cpp:223)
 	}
-done:
+save:
 	S.cler = cler; S.vertex_count = vcount; S.start = start; S.end = end;
 	S.nfront = nfront; S.norder = norder; S.cursor = cursor; S.ndelayed = ndel;
 	S.cw = cw; S.cw_next = cwn; S.splitpos = splitpos;
 	S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.cv0 = v0; S.cv1 = v1; S.cv2 = v2; S.cprev = prev; S.cnext = next;
 	S.g = g; S.fflush = fflush;
 	return rc;
-#undef CRT_NEXT_CLER
+#undef CRT_FETCH
 #undef CRT_SET_NEXT
 #undef CRT_SET_PREV
 #undef CRT_SET_DEL

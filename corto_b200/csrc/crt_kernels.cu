@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 	const uint32_t lane = threadIdx.x;
 	SmemRings rg;
 	const uint32_t oA = 0, oB = R*16u, oQ = oB + R*8u, oF = oQ + Q*4u, oP = oF + CLERS_STAGE*16u;
-	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(crt_smem);
+	uint32_t sbase;   // opaque move: keeps the shared-window base in a register instead of re-deriving it at every access
+	asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(crt_smem)));
 	rg.aA = sbase + oA; rg.aB = sbase + oB; rg.aQ = sbase + oQ; rg.aF = sbase + oF; rg.aP = sbase + oP;
 	rg.RM = R - 1; rg.QM = Q - 1; rg.FM = CLERS_STAGE - 1; rg.PM = CLERS_STAGE - 1;
 	const uint32_t W = R - 3u*CLERS_BUDGET, QW = Q - 3u*CLERS_BUDGET;
@@ -344,9 +345,11 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 		io.pred = (uint32_t *)M->pred_ptr;
 		ClersState S;
 		clers_state_init(S, io);
+		int splitbits;
+		asm volatile("mov.u32 %0, %1;" : "=r"(splitbits) : "r"(ilog2_u32(io.nvert) + 1));
 		int rc = 0;
 		for(;;) {
-			if(lane == 0) rc = clers_run(io, rg, S, CLERS_BUDGET);
+			if(lane == 0) rc = clers_run(io, rg, S, CLERS_BUDGET, splitbits);
 			rc = __shfl_sync(0xffffffffu, rc, 0);
 			// ---- cooperative drain (all lanes) ----
 			const uint32_t f0 = __shfl_sync(0xffffffffu, S.fflush, 0), f1 = __shfl_sync(0xffffffffu, S.start, 0);

@@ -70,7 +70,7 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		const uint32_t W = R - 3u*budget, QW = Q - 3u*budget;
 		ClersState S; clers_state_init(S, io);
 		for(int guard = 0; guard < (1 << 30); guard++) {
-			rc = clers_run(io, rg, S, budget);
+			rc = clers_run(io, rg, S, budget, ilog2_u32(io.nvert) + 1);
 			for(uint32_t f = S.fflush; f < S.start; f++) { const uint4_t v = sf[f & (ST - 1)]; faces[(size_t)f*3] = v.x; faces[(size_t)f*3 + 1] = v.y; faces[(size_t)f*3 + 2] = v.z; }
 			for(uint32_t v = S.pflush; v < S.vertex_count; v++) { const uint4_t x = sp[v & (ST - 1)]; pred[(size_t)v*4] = x.x; pred[(size_t)v*4 + 1] = x.y; pred[(size_t)v*4 + 2] = x.z; pred[(size_t)v*4 + 3] = 0; }
 			S.fflush = S.start; S.pflush = S.vertex_count;
