@@ -396,8 +396,79 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 }
 
 // =========================================================================================================
-// K5  mesh delta inverse (serial in vertex order: v[i] depends on earlier vertices chosen by the topology)
+// K5  mesh delta inverse.  v[i] += v[a] + v[b] - v[c] (parallelogram) or v[i] += v[a], with a,b,c < i chosen by the
+//     topology: a recurrence on a DAG.  A warp takes 32 consecutive vertices per round, lane = vertex:
+//       1. every lane loads its prediction and residual, and gathers the operands that lie OUTSIDE the block from
+//          global memory — 32 vertices' worth of independent loads in flight at once (the serial v1 kernel paid one L2
+//          round trip per vertex);
+//       2. operands INSIDE the block are resolved in registers: when the block is a pure chain (a = i-1, b and c outside:
+//          99.7 % of a grid) the recurrence is an inclusive warp scan; otherwise a 32-step shuffle loop
+//          reproduces the sequential order exactly (a not-yet-processed operand is still its residual, as in the
+//          in-place reference loop, vertex_attribute.h:165-176).
 // =========================================================================================================
+template <typename T, int NC>
+__device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint32_t nvert, bool par, int lane) {
+	for(uint32_t base = 0; base < nvert; base += 32) {
+		const uint32_t i = base + lane;
+		const bool in = i < nvert;
+		const bool act = in && i > 0;                 // vertex 0 keeps its residual (loops start at 1)
+		uint4 p = in ? pred[i] : make_uint4(0, 0, 0, 0);
+		const uint32_t a = p.x, b = p.y, c = p.z;
+		uint32_t x[NC], fa[NC], fb[NC], fc[NC];
+		const bool a_in = act && (a - base) < 32u, b_in = act && par && (b - base) < 32u, c_in = act && par && (c - base) < 32u;
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			x[k] = in ? (uint32_t)v[(size_t)i*NC + k] : 0u;
+			fa[k] = (act && !a_in && a < nvert) ? (uint32_t)v[(size_t)a*NC + k] : 0u;
+			fb[k] = (act && par && !b_in && b < nvert) ? (uint32_t)v[(size_t)b*NC + k] : 0u;
+			fc[k] = (act && par && !c_in && c < nvert) ? (uint32_t)v[(size_t)c*NC + k] : 0u;
+		}
+		// pure chain: every in-block operand is "a = previous lane"
+		const bool chain_ok = !act || (!b_in && !c_in && (!a_in || a == i - 1));
+		if(__all_sync(0xffffffffu, chain_ok)) {
+#pragma unroll
+			for(int k = 0; k < NC; k++) {
+				// r = everything except the in-block a term; lanes whose a is outside (or inactive) start a new segment
+				uint32_t r = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k];
+				const bool head = !a_in;                   // segment head: does not add the previous lane
+				// segmented inclusive scan: value + flag
+				uint32_t val = r; bool flag = head;
+#pragma unroll
+				for(int d = 1; d < 32; d <<= 1) {
+					const uint32_t ov = __shfl_up_sync(0xffffffffu, val, d);
+					const bool of = __shfl_up_sync(0xffffffffu, (int)flag, d) != 0;
+					if(lane >= d && !flag) { val += ov; flag = of; }
+				}
+				x[k] = val;
+			}
+		} else {
+			for(int j = 0; j < 32; j++) {
+				const uint32_t aj = __shfl_sync(0xffffffffu, a, j), bj = __shfl_sync(0xffffffffu, b, j), cj = __shfl_sync(0xffffffffu, c, j);
+				const int fl = __shfl_sync(0xffffffffu, (int)act | ((int)a_in << 1) | ((int)b_in << 2) | ((int)c_in << 3), j);
+				if(!(fl & 1)) continue;
+#pragma unroll
+				for(int k = 0; k < NC; k++) {
+					// x of an in-block lane is final if that lane was processed already, else still its residual: exactly what
+					// the in-place sequential loop would read
+					const uint32_t xa = __shfl_sync(0xffffffffu, x[k], (aj - base) & 31u);
+					const uint32_t xb = __shfl_sync(0xffffffffu, x[k], (bj - base) & 31u);
+					const uint32_t xc = __shfl_sync(0xffffffffu, x[k], (cj - base) & 31u);
+					if(lane == j) {
+						uint32_t r = x[k] + ((fl & 2) ? xa : fa[k]);
+						if(par) r = r + ((fl & 4) ? xb : fb[k]) - ((fl & 8) ? xc : fc[k]);
+						x[k] = r;
+					}
+				}
+			}
+		}
+		if(act) {
+#pragma unroll
+			for(int k = 0; k < NC; k++) v[(size_t)i*NC + k] = (T)x[k];
+		}
+		__syncwarp();
+	}
+}
+
 __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work, uint32_t nwork) {
 	const uint32_t w = blockIdx.x;
 	if(w >= nwork) return;
@@ -408,37 +479,22 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 	const uint32_t nvert = M->nvert;
 	const uint4 *pred = (const uint4 *)M->pred_ptr;
 	const int nc = A->ncomp;
-	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;
-	const bool active = lane < nc;
+	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;    // normals: d += d[a] only (normal_attribute.cpp:193-201)
 	if(A->codec == CODEC_COLOR) {
 		uint8_t *v = (uint8_t *)A->work_ptr;
-		for(uint32_t base = 0; base < nvert; base += 32) {
-			uint4 p = (base + lane < nvert) ? pred[base + lane] : make_uint4(0, 0, 0, 0);
-			const uint32_t cnt = min(32u, nvert - base);
-			for(uint32_t j = 0; j < cnt; j++) {
-				const uint32_t a = __shfl_sync(0xffffffffu, p.x, j), b = __shfl_sync(0xffffffffu, p.y, j), c = __shfl_sync(0xffffffffu, p.z, j);
-				const uint32_t i = base + j;
-				if(i == 0 || !active) continue;
-				uint32_t x = v[(size_t)i*nc + lane];
-				if(par) x = x + v[(size_t)a*nc + lane] + v[(size_t)b*nc + lane] - v[(size_t)c*nc + lane];
-				else x = x + v[(size_t)a*nc + lane];
-				v[(size_t)i*nc + lane] = (uint8_t)x;
-			}
+		switch(nc) {
+		case 1: delta_mesh_rounds<uint8_t, 1>(v, pred, nvert, par, lane); break;
+		case 2: delta_mesh_rounds<uint8_t, 2>(v, pred, nvert, par, lane); break;
+		case 3: delta_mesh_rounds<uint8_t, 3>(v, pred, nvert, par, lane); break;
+		default: delta_mesh_rounds<uint8_t, 4>(v, pred, nvert, par, lane); break;
 		}
 	} else {
 		uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
-		for(uint32_t base = 0; base < nvert; base += 32) {
-			uint4 p = (base + lane < nvert) ? pred[base + lane] : make_uint4(0, 0, 0, 0);
-			const uint32_t cnt = min(32u, nvert - base);
-			for(uint32_t j = 0; j < cnt; j++) {
-				const uint32_t a = __shfl_sync(0xffffffffu, p.x, j), b = __shfl_sync(0xffffffffu, p.y, j), c = __shfl_sync(0xffffffffu, p.z, j);
-				const uint32_t i = base + j;
-				if(i == 0 || !active) continue;
-				uint32_t x = v[(size_t)i*nc + lane];
-				if(par) x = x + v[(size_t)a*nc + lane] + v[(size_t)b*nc + lane] - v[(size_t)c*nc + lane];
-				else x = x + v[(size_t)a*nc + lane];
-				v[(size_t)i*nc + lane] = x;
-			}
+		switch(nc) {
+		case 1: delta_mesh_rounds<uint32_t, 1>(v, pred, nvert, par, lane); break;
+		case 2: delta_mesh_rounds<uint32_t, 2>(v, pred, nvert, par, lane); break;
+		case 3: delta_mesh_rounds<uint32_t, 3>(v, pred, nvert, par, lane); break;
+		default: delta_mesh_rounds<uint32_t, 4>(v, pred, nvert, par, lane); break;
 		}
 	}
 }
