@@ -1,0 +1,201 @@
+"""CPU tests of the product's host side (no GPU): the C ABI library loads and exports every declared symbol, header
+parsing / directory walk / error behaviour mirror the reference, the device cores pass on the CPU (host emulation),
+and the multi-rank sharding works over gloo with world_size 2."""
+import ctypes as C
+import glob
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import corto_b200
+from tests import cases
+from oracle import pyoracle, refshim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _golden(name):
+    return refshim.aligned_blob(open(os.path.join(GOLDEN, name + ".crt"), "rb").read())
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "corto_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", hdr))
+    names -= {"defined"}
+    assert len(names) > 60
+    lib = C.CDLL(corto_b200.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device decode must fail loudly (CRT_E_CUDA), never fall back to a CPU path."""
+    if corto_b200.device_available():
+        pytest.skip("a GPU is visible here")
+    d = corto_b200.Decoder(_golden("grid_est"))
+    with pytest.raises(corto_b200.CortoError) as e:
+        d.decode()
+    assert e.value.code == -9
+
+
+def test_product_does_not_touch_the_oracle():
+    for path in glob.glob(os.path.join(ROOT, "corto_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            src = open(path, errors="replace").read()
+            assert "liboracle" not in src and "pyoracle" not in src and "refshim" not in src and "libcorto_ref" not in src, path
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.SMALL])
+def test_header_matches_reference_ctor(name):
+    """crt::Decoder ctor fields (decoder.cpp:41-89): nvert, nface, attribute table in wire order."""
+    blob = _golden(name)
+    d = corto_b200.Decoder(blob)
+    i = pyoracle.info(blob)
+    assert (d.nvert, d.nface) == (i["nvert"], i["nface"])
+    assert list(d.attributes) == [a["name"] for a in i["attrs"]]
+    for a in i["attrs"]:
+        mine = d.attributes[a["name"]]
+        assert (mine["codec"], mine["N"], mine["strategy"]) == (a["codec"], a["N"], a["strategy"])
+        assert np.float32(mine["q"]) == np.float32(a["q"])
+    g = d.groups
+    assert g and g[-1]["end"] == d.nface or d.nface == 0
+
+
+def test_groups_and_properties():
+    d = corto_b200.Decoder(_golden("groups3"))
+    g = d.groups
+    assert len(g) == 3 and [x["end"] for x in g] == sorted(x["end"] for x in g) and g[-1]["end"] == d.nface
+    assert g[1]["properties"] == {"material": "m1"}      # oracle/ref_shim.cpp gives odd groups a material property
+
+
+def test_error_behaviour():
+    blob = _golden("grid_pos")
+    L = corto_b200.lib()
+    bad = blob.copy(); bad[0] ^= 0xFF
+    assert not L.crt_new_decoder(len(bad), bad.ctypes.data_as(C.c_void_p))
+    assert b"Not a crt file" in L.crt_last_error()                           # decoder.cpp:50-51
+    raw = np.empty(len(blob) + 8, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 4 + 1                                         # misaligned by one
+    mis = raw[off:off + len(blob)]; mis[:] = blob
+    assert not L.crt_new_decoder(len(mis), mis.ctypes.data_as(C.c_void_p))
+    assert b"alignegned" in L.crt_last_error()                               # decoder.cpp:43-44 (sic)
+
+
+@pytest.mark.parametrize("name", ["grid_est", "cloud_all", "none_entropy", "torus"])
+def test_truncated_blobs_are_rejected_not_read_out_of_bounds(name):
+    """The reference has no bounds checks; the directory walk must reject every truncation."""
+    blob = _golden(name)
+    L = corto_b200.lib()
+    for cut in list(range(0, 64)) + list(range(64, len(blob) - 1, max(1, len(blob) // 97))):
+        part = refshim.aligned_blob(blob[:cut].tobytes())
+        ptrs = (C.c_void_p * 1)(part.ctypes.data)
+        lens = (C.c_int * 1)(cut)
+        h = L.crt_batch_create(1, ptrs, lens)
+        assert not h, "truncated at %d of %d accepted" % (cut, len(blob))
+    ptrs = (C.c_void_p * 1)(blob.ctypes.data)
+    lens = (C.c_int * 1)(len(blob))
+    h = L.crt_batch_create(1, ptrs, lens)
+    assert h
+    L.crt_batch_destroy(h)
+
+
+def test_batch_layout_without_gpu():
+    blobs = [_golden(n) for n in ("grid_est", "cloud_all", "torus", "triangle")]
+    bd_ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+    lens = (C.c_int * len(blobs))(*[len(b) for b in blobs])
+    L = corto_b200.lib()
+    h = L.crt_batch_create(len(blobs), bd_ptrs, lens)
+    assert h
+    vb, fb = L.crt_batch_vert_base(h), L.crt_batch_face_base(h)
+    nv = [pyoracle.info(b)["nvert"] for b in blobs]
+    nf = [pyoracle.info(b)["nface"] for b in blobs]
+    assert [vb[i] for i in range(5)] == list(np.concatenate([[0], np.cumsum(nv)]))
+    assert [fb[i] for i in range(5)] == list(np.concatenate([[0], np.cumsum(nf)]))
+    assert L.crt_batch_total_bytes(h) == sum(len(b) for b in blobs)
+    L.crt_batch_destroy(h)
+
+
+# ---- the kernels' sequential cores on the CPU ------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(ROOT, "tests", "host_emul", "libhost_emul.so")
+    src = [os.path.join(ROOT, "tests", "host_emul", "host_emul.cpp"), os.path.join(ROOT, "corto_b200", "csrc", "crt_walk.cpp")]
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so] + src)
+    return C.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.SMALL])
+def test_device_cores_on_cpu(emul, name):
+    """tun_build_seq vs the oracle's dictionaries for every entropy block; clers_decode_seq and clers_run (the kernel's
+    lazy-front machine, with tiny rings so that every reach-back / drain path runs) vs the oracle's faces + predictions."""
+    blob = _golden(name)
+    out = np.zeros(64 * 5, dtype=np.uint32)
+    n = emul.emul_walk_blocks(_p(blob), len(blob), _p(out), 64)
+    assert n > 0
+    for po, nsym, size, csize, do in out[:n * 5].reshape(n, 5).tolist():
+        if nsym <= 1:
+            continue
+        probs = np.ascontiguousarray(blob[po:po + 2 * nsym])
+        i1, l1, t1, u1 = pyoracle.tunstall_tables(probs)
+        i2 = np.zeros(256, np.int32); l2 = np.zeros(256, np.int32); t2 = np.zeros(8192, np.uint8)
+        emul.emul_tunstall_tables(_p(probs), nsym, _p(i2), _p(l2), _p(t2))
+        assert np.array_equal(i1, i2) and np.array_equal(l1, l2) and np.array_equal(t1[:u1], t2[:u1])
+    o = pyoracle.decode(blob, debug=True)
+    if o["nface"]:
+        for ring in ((0, 0), (-64, 64), (-128, 64), (-4096, 2048)):
+            faces = np.zeros((o["nface"], 3), np.uint32); pred = np.zeros((o["nvert"], 3), np.uint32)
+            rc = emul.emul_clers(_p(blob), len(blob), _p(o["clers"]), len(o["clers"]), _p(faces), _p(pred), ring[0], ring[1])
+            assert rc == 0 and np.array_equal(faces, o["index"]) and np.array_equal(pred[1:], o["prediction"][1:]), (name, ring)
+
+
+# ---- multi-rank sharding over gloo, world_size 2 ---------------------------------------------------------------------
+def test_shard_lpt_balances():
+    rs = np.random.RandomState(1)
+    nv = rs.randint(8000, 256000, 512).astype(np.uint32)
+    nf = (nv * 2).astype(np.uint32)
+    na = np.full(512, 4, dtype=np.uint32)
+    for world in (1, 2, 4, 8):
+        r = corto_b200.shard_lpt(nv, nf, na, world)
+        assert r.min() == 0 and r.max() == world - 1
+        load = np.array([(4.0 * nf[r == k] + nv[r == k] * 4.0).sum() for k in range(world)])
+        assert load.max() / load.mean() < 1.02
+
+
+def test_scatter_two_ranks_gloo(tmp_path):
+    """corto_b200.dist.scatter_blobs: rank 0 holds the blobs, LPT-shards them, every rank receives exactly its bin."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, glob, hashlib
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from corto_b200 import dist as cd
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+paths = sorted(glob.glob(os.path.join(%r, "*.crt")))
+blobs = [np.frombuffer(open(p, "rb").read(), dtype=np.uint8) for p in paths] if rank == 0 else None
+mine, ids = cd.scatter_blobs(blobs, src=0, device="cpu")
+all_ids = [None] * world
+dist.all_gather_object(all_ids, ids)
+flat = sorted(i for x in all_ids for i in x)
+assert flat == list(range(len(paths))), flat
+for b, i in zip(mine, ids):
+    assert hashlib.sha1(b.tobytes()).hexdigest() == hashlib.sha1(open(paths[i], "rb").read()).hexdigest()
+assert len(mine) > 0
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok", len(mine))
+''' % (ROOT, GOLDEN))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
