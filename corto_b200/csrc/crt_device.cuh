@@ -603,6 +603,272 @@ save:
 #undef CRT_MATERIALISE
 }
 
+// ---- CLERS automaton, v4: leader / follower ------------------------------------------------------------------------
+// The machine has two kinds of state: LINKS (which edge comes next: prev/next/deleted, the FIFO, the symbol stream) and
+// LABELS (which vertices an edge carries: v0,v1,v2 -> faces, predictions).  Labels never influence links
+// (decoder.cpp:204-358: every branch depends on the symbol, `deleted`, and the queues only), so the serial chain that
+// limits throughput is the link machine alone.  v4 runs it as the LEADER in one warp and streams a log of what it did
+// (one 32-bit word per event) through a shared-memory ring to the FOLLOWER in a second warp (its own SM sub-partition),
+// which replays the log on labels only: allocates vertex ids, reads split indices, emits faces and predictions.
+// Both are lane-0 machines; the remaining lanes of each warp do the coalesced drains.
+// Log word: type << 28 | id.
+enum { LG_TV = 0, LG_TS = 1, LG_V = 2, LG_S = 3, LG_L = 4, LG_R = 5, LG_E = 6, LG_P = 7, LG_M = 8, LG_G = 9 };
+constexpr uint32_t CLERS_DEL = 0x80000000u;       // `deleted` lives in the top bit of an edge's prev link
+constexpr uint32_t CLERS_NOLINK = 0x7FFFFFFFu;    // placeholder for a link that is still deferred
+
+struct LeadState {
+	uint32_t cler; uint64_t cw, cw_next;
+	uint32_t g, start, end;
+	uint32_t nfront, norder, cursor, ndelayed;
+	uint32_t have, lp, ln, cf, cprev, cnext;
+	uint32_t eflush, qflush;
+	uint32_t nlog;
+};
+CRT_HD void lead_init(LeadState &S, const ClersIO &io) {
+	S.cler = 0; S.cw = io.nclers ? load_u64(io.clers) : 0; S.cw_next = io.nclers > 8 ? load_u64(io.clers + 8) : 0;
+	S.g = 0; S.start = S.end = 0; S.nfront = S.norder = S.cursor = S.ndelayed = 0;
+	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.cprev = S.cnext = 0; S.eflush = S.qflush = 0; S.nlog = 0;
+}
+
+CRT_COLD static uint2_t lead_g_load(const EdgeB *eb, uint32_t x) { const EdgeB l = eb[x]; return uint2_t{l.prev, l.next}; }
+
+// Link machine.  Consumes at most `budget` symbols (every symbol yields at most 2 log words, a pop 1).  Returns 1 when all
+// groups are done, 0 to be called again after the caller drained / waited for log space, < 0 on a topology error.
+template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &S, int budget) {
+	uint32_t cler = S.cler, start = S.start, end = S.end;
+	uint32_t nfront = S.nfront, norder = S.norder, cursor = S.cursor, ndel = S.ndelayed, nlog = S.nlog;
+	uint64_t cw = S.cw, cwn = S.cw_next;
+	uint32_t have = S.have, lp = S.lp, ln = S.ln, f = S.cf, prev = S.cprev, next = S.cnext, g = S.g;
+	const uint32_t eflush = S.eflush, qflush = S.qflush, nclers = io.nclers, cap = io.cap;
+	uint32_t n = nclers - cler;
+	if(n > (uint32_t)budget) n = (uint32_t)budget;
+	int rc = 0;
+#define LD_FETCH(c)                                                                                      \
+	do {                                                                                                 \
+		c = (uint32_t)cw & 0xffu; cw >>= 8; cler++;                                                      \
+		if((cler & 7u) == 0) { cw = cwn; cwn = (cler + 8 < nclers) ? load_u64(io.clers + cler + 8) : 0; } \
+	} while(0)
+#define LD_LOG(t, id) do { rg.stLog(nlog, ((uint32_t)(t) << 28) | (id)); nlog++; } while(0)
+#define LD_SET_NEXT(x, v) do { if((x) >= eflush) rg.stB_next(x, v); else clers_g_set_next(io.eb, x, v); } while(0)
+#define LD_SET_PREV(x, v) do { if((x) >= eflush) rg.stB_prev(x, v); else clers_g_set_prev(io.eb, x, v); } while(0)
+#define LD_LOADB(ID_, P_, Q_) do { if((ID_) >= eflush) rg.ldB(ID_, P_, Q_); else { const uint2_t t_ = lead_g_load(io.eb, ID_); P_ = t_.x; Q_ = t_.y; } } while(0)
+#define LD_MATERIALISE()                                                                                 \
+	do {                                                                                                 \
+		if(nfront >= cap) return -5;                                                                     \
+		f = nfront++;                                                                                    \
+		rg.stB(f, prev, next);                                                                           \
+		if(lp) LD_SET_NEXT(prev, f);                                                                     \
+		if(ln) LD_SET_PREV(next, f);                                                                     \
+		lp = ln = 0;                                                                                     \
+		LD_LOG(LG_M, f);                                                                                 \
+	} while(0)
+	for(;;) {
+		if(!have) {
+			if(start >= end) {                         // next group: fresh front (decoder.cpp:173-178, 207-221)
+				if(g >= io.ngroups) { rc = 1; break; }
+				uint32_t e = io.group_ends[g];
+				if(e > io.nface) e = io.nface;
+				uint32_t st = g ? io.group_ends[g - 1] : 0;
+				if(st > io.nface) st = io.nface;
+				g++;
+				start = st; end = e;
+				nfront = norder = cursor = ndel = 0;
+				LD_LOG(LG_G, g - 1);
+				if(eflush | qflush) { S.eflush = 0; S.qflush = 0; rc = 0; break; }   // rings restart: reset the flushed limits first
+				continue;
+			}
+			uint32_t dead = 1, p = 0, q = 0;
+			while(cursor < norder) {                   // FIFO, skipping edges deleted since they were queued
+				f = (cursor >= qflush) ? rg.ldQ(cursor) : io.order[cursor];
+				cursor++;
+				LD_LOADB(f, p, q);
+				dead = p & CLERS_DEL;
+				if(!dead) break;
+			}
+			if(dead && ndel) {
+				f = io.delayed[--ndel];
+				LD_LOADB(f, p, q);
+				dead = p & CLERS_DEL;
+				if(dead) continue;
+			}
+			if(!dead) { prev = p; next = q; lp = ln = 0; have = 1; LD_LOG(LG_P, f); }
+			else {                                     // nothing pending: start triangle
+				if(n == 0) { rc = (cler >= nclers) ? -5 : 0; break; }
+				n--;
+				if(nfront + 3 > cap) return -5;
+				uint32_t c;
+				LD_FETCH(c);
+				const uint32_t b = nfront;
+				rg.stB(b, b + 2, b + 1); rg.stB(b + 1, b + 0, b + 2); rg.stB(b + 2, b + 1, b + 0);
+				rg.stQ(norder, b); rg.stQ(norder + 1, b + 1); rg.stQ(norder + 2, b + 2);
+				norder += 3; nfront += 3;
+				LD_LOG(c == C_SPLIT ? LG_TS : LG_TV, b);
+				start += 1;
+				continue;
+			}
+		}
+		do {
+			if(n == 0) { rc = (cler >= nclers) ? -5 : 0; goto save; }
+			n--;
+			uint32_t c;
+			LD_FETCH(c);
+			if(c == C_VERTEX || c == C_SPLIT) {
+				if(nfront >= cap) return -5;
+				const uint32_t b = nfront++;
+				rg.stB(b, CLERS_NOLINK, next);             // second new edge: persistent, queued; its prev link is deferred
+				LD_SET_PREV(next, b);
+				rg.stQ(norder, b); norder++;
+				LD_LOG(c == C_VERTEX ? LG_V : LG_S, b);
+				start++;
+				next = b; lp = 1; ln = 1; f = CLERS_NOID;
+			} else if(c == C_LEFT) {
+				if((lp | ln) && prev == next) LD_MATERIALISE();
+				uint32_t pp, pn;
+				LD_LOADB(prev, pp, pn);
+				(void)pn;
+				LD_SET_PREV(prev, pp | CLERS_DEL);
+				LD_LOG(LG_L, prev);
+				start++;
+				prev = pp & ~CLERS_DEL; lp = 1; ln = 1; f = CLERS_NOID;
+			} else if(c == C_RIGHT) {
+				if((lp | ln) && prev == next) LD_MATERIALISE();
+				uint32_t np, nn;
+				LD_LOADB(next, np, nn);
+				LD_SET_PREV(next, np | CLERS_DEL);
+				LD_LOG(LG_R, next);
+				start++;
+				next = nn; lp = 1; ln = 1; f = CLERS_NOID;
+			} else if(c == C_BOUNDARY) {
+				if(f == CLERS_NOID) LD_MATERIALISE();
+				have = 0; break;
+			} else if(c == C_DELAY) {
+				if(f == CLERS_NOID) LD_MATERIALISE();
+				io.delayed[ndel++] = f;
+				have = 0; break;
+			} else if(c == C_END) {
+				if((lp | ln) && prev == next) LD_MATERIALISE();
+				uint32_t pp, pn, np, nn;
+				LD_LOADB(prev, pp, pn);
+				LD_LOADB(next, np, nn);
+				(void)pn;
+				LD_SET_PREV(prev, pp | CLERS_DEL);
+				LD_SET_PREV(next, np | CLERS_DEL);
+				LD_SET_NEXT(pp & ~CLERS_DEL, nn);
+				LD_SET_PREV(nn, pp & ~CLERS_DEL);
+				LD_LOG(LG_E, prev);
+				start++;
+				have = 0; break;
+			} else return -5;
+		} while(start < end);
+		have = 0;
+	}
+save:
+	S.cler = cler; S.start = start; S.end = end; S.nfront = nfront; S.norder = norder; S.cursor = cursor; S.ndelayed = ndel;
+	S.cw = cw; S.cw_next = cwn; S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.cprev = prev; S.cnext = next; S.g = g; S.nlog = nlog;
+	return rc;
+#undef LD_FETCH
+#undef LD_LOG
+#undef LD_SET_NEXT
+#undef LD_SET_PREV
+#undef LD_LOADB
+#undef LD_MATERIALISE
+}
+
+struct FollowState {
+	uint32_t v0, v1, v2;               // labels of the current edge
+	uint32_t vcount, nfaces;           // vertices created / faces emitted so far
+	uint64_t splitpos;
+	uint32_t gstart;                   // face index where the current group starts (for malformed group tables)
+	uint32_t aflush, amax;             // label ids below aflush live in global memory; amax = ids written so far
+	uint32_t fflush, pflush;           // faces / predictions already drained
+	uint32_t tail;                     // log words consumed
+};
+CRT_HD void follow_init(FollowState &S) {
+	S.v0 = S.v1 = S.v2 = 0; S.vcount = 0; S.nfaces = 0; S.splitpos = 0; S.gstart = 0; S.aflush = S.amax = 0; S.fflush = S.pflush = 0; S.tail = 0;
+}
+CRT_COLD static uint4_t follow_g_load(const EdgeA *ea, uint32_t x) { const EdgeA a = ea[x]; return uint4_t{a.v0, a.v1, a.v2, 0}; }
+
+// Label machine: replays log words [S.tail, upto).  Stops early (returns 0 with S.tail < upto) when a staging ring is
+// full (`room` entries left at call time) so the caller can drain; returns 0 normally, < 0 on an inconsistent stream.
+template <class RG> CRT_HD int clers_follow(const ClersIO &io, RG &rg, FollowState &S, uint32_t upto, uint32_t room, int splitbits) {
+	uint32_t v0 = S.v0, v1 = S.v1, v2 = S.v2, vcount = S.vcount, nf = S.nfaces, tail = S.tail, amax = S.amax;
+	uint64_t splitpos = S.splitpos;
+	const uint32_t aflush = S.aflush, nvert = io.nvert, nface = io.nface;
+	int rc = 0;
+#define FW_LOADA(ID_, A_, B_, C_) do { if((ID_) >= aflush) rg.ldA(ID_, A_, B_, C_); else { const uint4_t t_ = follow_g_load(io.ea, ID_); A_ = t_.x; B_ = t_.y; C_ = t_.z; } } while(0)
+	while(tail < upto && room >= 3) {
+		const uint32_t w = rg.ldLog(tail); tail++;
+		const uint32_t t = w >> 28, id = w & 0x0FFFFFFFu;
+		if(t == LG_V || t == LG_S) {
+			uint32_t opp;
+			if(t == LG_V) {
+				if(vcount >= nvert) { rc = -5; break; }
+				rg.stP(vcount, v1, v0, v2);
+				opp = vcount++;
+			} else {
+				opp = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+				if(opp >= nvert) { rc = -5; break; }
+			}
+			if(nf >= nface) { rc = -5; break; }
+			rg.stA(id, opp, v1, v0); amax = id + 1;
+			rg.stF(nf, v1, v0, opp); nf++;
+			v2 = v1; v1 = opp;
+			room--;
+		} else if(t == LG_L) {
+			uint32_t a, b, c;
+			FW_LOADA(id, a, b, c); (void)b; (void)c;
+			if(nf >= nface) { rc = -5; break; }
+			rg.stF(nf, v1, v0, a); nf++;
+			v2 = v0; v0 = a;
+			room--;
+		} else if(t == LG_R) {
+			uint32_t a, b, c;
+			FW_LOADA(id, a, b, c); (void)a; (void)c;
+			if(nf >= nface) { rc = -5; break; }
+			rg.stF(nf, v1, v0, b); nf++;
+			v2 = v1; v1 = b;
+			room--;
+		} else if(t == LG_P) {
+			FW_LOADA(id, v0, v1, v2);
+		} else if(t == LG_M) {
+			rg.stA(id, v0, v1, v2); amax = id + 1;
+		} else if(t == LG_E) {
+			uint32_t a, b, c;
+			FW_LOADA(id, a, b, c); (void)b; (void)c;
+			if(nf >= nface) { rc = -5; break; }
+			rg.stF(nf, v1, v0, a); nf++;
+			room--;
+		} else if(t == LG_TV || t == LG_TS) {          // start triangle (decoder.cpp:224-259)
+			uint32_t last = vcount - 1, vi[3], mask = 0;
+			if(t == LG_TS) { mask = getbits(io.split, io.split_nwords, splitpos, 3); splitpos += 3; }
+			for(int k = 0; k < 3; k++) {
+				uint32_t v;
+				if(mask & (1u << k)) {
+					v = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+					if(v >= nvert) { rc = -5; break; }
+				} else {
+					if(vcount >= nvert) { rc = -5; break; }
+					rg.stP(vcount, last, last, last);
+					last = v = vcount++;
+				}
+				vi[k] = v;
+			}
+			if(rc || nf >= nface) { rc = -5; break; }
+			rg.stF(nf, vi[0], vi[1], vi[2]); nf++;
+			rg.stA(id, vi[1], vi[2], vi[0]); rg.stA(id + 1, vi[2], vi[0], vi[1]); rg.stA(id + 2, vi[0], vi[1], vi[2]); amax = id + 3;
+			room -= 3;
+		} else if(t == LG_G) {                         // group restart: label ids start over; a malformed table may move the face cursor
+			uint32_t st = id ? io.group_ends[id - 1] : 0;
+			if(st > nface) st = nface;
+			if(st != nf || S.aflush) { S.tail = tail - 1; S.gstart = st; rc = 2; break; }   // caller drains, resets aflush / nf, replays the word
+		} else { rc = -5; break; }
+	}
+#undef FW_LOADA
+	if(rc != 2) S.tail = tail;
+	S.v0 = v0; S.v1 = v1; S.v2 = v2; S.vcount = vcount; S.nfaces = nf; S.splitpos = splitpos; S.amax = amax;
+	return rc;
+}
+
 // Plain-array ring policy (tests/host_emul; the kernel has its own shared-memory policy with the same interface).
 struct ArrayRings {
 	uint4_t *ra; uint2_t *rb; uint32_t *rq; uint4_t *sf; uint4_t *sp;
@@ -618,6 +884,12 @@ struct ArrayRings {
 	CRT_HD void stQ(uint32_t i, uint32_t v) { rq[i & QM] = v; }
 	CRT_HD void stF(uint32_t face, uint32_t a, uint32_t b, uint32_t c) { sf[face & FM] = uint4_t{a, b, c, 0}; }
 	CRT_HD void stP(uint32_t v, uint32_t a, uint32_t b, uint32_t c) { sp[v & PM] = uint4_t{a, b, c, 0}; }
+	// v4 (leader / follower) extras: 3-word labels in `ra` with their own mask, log ring
+	uint32_t *lg; uint32_t LM, AM;
+	CRT_HD void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const { const uint4_t v = ra[id & AM]; a = v.x; b = v.y; c = v.z; }
+	CRT_HD void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c) { ra[id & AM] = uint4_t{a, b, c, 0}; }
+	CRT_HD void stLog(uint32_t i, uint32_t w) { lg[i & LM] = w; }
+	CRT_HD uint32_t ldLog(uint32_t i) const { return lg[i & LM]; }
 };
 
 }  // namespace crtb

@@ -18,6 +18,7 @@
 //                vertex_attribute.h:184-230, normal_attribute.cpp:257-279, color_attribute.cpp:76-95
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "crt_device.cuh"
 #include "crt_kernels.h"
 
@@ -396,6 +397,183 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 }
 
 // =========================================================================================================
+// K4b  CLERS automaton, leader / follower (clers_lead + clers_follow, crt_device.cuh): two warps per mesh.
+//      warp 0: lane 0 = link machine (the serial chain), all lanes = write-back of link-ring entries leaving the window
+//      warp 1: lane 0 = label machine replaying the leader's log, all lanes = coalesced drains of faces / predictions and
+//              write-back of label-ring entries.
+//      The warps live on different SM sub-partitions, talk through a shared-memory log ring + head/tail words, and never
+//      share global state.  Every spin is bounded; a stuck partner turns into CRT_E_TOPOLOGY, not a hang.
+// =========================================================================================================
+struct SmemRings4 {
+	uint32_t aB, aQ, aL, aA, aF, aP;      // shared-space byte addresses
+	uint32_t RM, QM, LM, AM, FM, PM;
+	__device__ __forceinline__ void ldB(uint32_t id, uint32_t &p, uint32_t &n) const {
+		asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(p), "=r"(n) : "r"(aB + ((id & RM) << 3)));
+	}
+	__device__ __forceinline__ void stB(uint32_t id, uint32_t p, uint32_t n) {
+		asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(aB + ((id & RM) << 3)), "r"(p), "r"(n) : "memory");
+	}
+	__device__ __forceinline__ void stB_prev(uint32_t id, uint32_t p) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3)), "r"(p) : "memory"); }
+	__device__ __forceinline__ void stB_next(uint32_t id, uint32_t n) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3) + 4u), "r"(n) : "memory"); }
+	__device__ __forceinline__ uint32_t ldQ(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aQ + ((i & QM) << 2))); return v; }
+	__device__ __forceinline__ void stQ(uint32_t i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aQ + ((i & QM) << 2)), "r"(v) : "memory"); }
+	__device__ __forceinline__ void stLog(uint32_t i, uint32_t w) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aL + ((i & LM) << 2)), "r"(w) : "memory"); }
+	__device__ __forceinline__ uint32_t ldLog(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aL + ((i & LM) << 2))); return v; }
+	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const {
+		uint32_t d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & AM) << 4)));
+	}
+	__device__ __forceinline__ void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aA + ((id & AM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
+	}
+	__device__ __forceinline__ void stF(uint32_t face, uint32_t a, uint32_t b, uint32_t c) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aF + ((face & FM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
+	}
+	__device__ __forceinline__ void stP(uint32_t v, uint32_t a, uint32_t b, uint32_t c) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aP + ((v & PM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
+	}
+};
+
+__device__ __forceinline__ uint32_t ld_vol_shared(const uint32_t *p) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v; }
+__device__ __forceinline__ void st_vol_shared(uint32_t *p, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory"); }
+
+constexpr int LF_BUDGET = 64;           // symbols per leader chunk / log words per follower batch
+constexpr uint32_t LF_STAGE = 256;      // staged faces / predictions (>= 3*LF_BUDGET)
+constexpr uint32_t LF_LOG = 1024;       // log ring words
+constexpr uint32_t LF_SPIN = 1u << 26;  // bound on every wait loop
+
+__global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
+                                                  uint32_t RB, uint32_t Q, uint32_t RA) {
+	__shared__ uint32_t ctl[8];          // 0 head, 1 tail, 2 done, 3 abort, 4 mesh, 5 lead rc
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	SmemRings4 rg;
+	const uint32_t oB = 0, oQ = oB + RB*8u, oL = oQ + Q*4u, oA = oL + LF_LOG*4u, oF = oA + RA*16u, oP = oF + LF_STAGE*16u;
+	uint32_t sbase;
+	asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(crt_smem)));
+	rg.aB = sbase + oB; rg.aQ = sbase + oQ; rg.aL = sbase + oL; rg.aA = sbase + oA; rg.aF = sbase + oF; rg.aP = sbase + oP;
+	rg.RM = RB - 1; rg.QM = Q - 1; rg.LM = LF_LOG - 1; rg.AM = RA - 1; rg.FM = LF_STAGE - 1; rg.PM = LF_STAGE - 1;
+	const uint32_t WB = RB - 3u*LF_BUDGET, QW = Q - 3u*LF_BUDGET, WA = RA - 3u*LF_BUDGET;
+	for(;;) {
+		__syncthreads();
+		if(threadIdx.x == 0) { ctl[4] = atomicAdd(ticket, 1u); ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; ctl[3] = 0; ctl[5] = 0; }
+		__syncthreads();
+		const uint32_t w = ctl[4];
+		if(w >= nwork) break;
+		const uint32_t mi = mesh_order[w];
+		const MeshDesc *M = B.mesh + mi;
+		const TunDesc td = B.tun[M->clers_tun];
+		ClersIO io;
+		io.clers = B.symbols + td.out_off; io.nclers = td.size;
+		io.split = (const uint32_t *)(B.blobs + M->split_off); io.split_nwords = M->split_nwords;
+		io.group_ends = B.group_ends + M->group0; io.ngroups = M->ngroups;
+		io.nvert = M->nvert; io.nface = M->nface;
+		const size_t slot = blockIdx.x;
+		io.cap = scratch.cap;
+		io.ea = scratch.ea + slot*scratch.cap; io.eb = scratch.eb + slot*scratch.cap;
+		io.order = scratch.order + slot*scratch.cap; io.delayed = scratch.delayed + slot*scratch.cap;
+		const uint32_t need = 3u*M->max_group_faces + 3u;
+		if(need < io.cap) io.cap = need;
+		io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
+		io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
+		io.pred = (uint32_t *)M->pred_ptr;
+		if(warp == 0) {
+			// ------------------------------------------------ leader ------------------------------------------------
+			LeadState S;
+			lead_init(S, io);
+			int rc = 0;
+			for(;;) {
+				if(lane == 0) {      // wait for log space (the follower is at most one ring behind)
+					uint32_t spins = 0;
+					while(S.nlog + 3u*LF_BUDGET + 8u - ld_vol_shared(&ctl[1]) > LF_LOG) {
+						if(ld_vol_shared(&ctl[3]) || ++spins > LF_SPIN) { rc = -5; break; }
+						__nanosleep(64);
+					}
+					if(rc == 0) rc = clers_lead(io, rg, S, LF_BUDGET);
+					__threadfence_block();
+					st_vol_shared(&ctl[0], S.nlog);
+				}
+				rc = __shfl_sync(0xffffffffu, rc, 0);
+				const uint32_t e0 = __shfl_sync(0xffffffffu, S.eflush, 0), nf = __shfl_sync(0xffffffffu, S.nfront, 0);
+				const uint32_t q0 = __shfl_sync(0xffffffffu, S.qflush, 0), no = __shfl_sync(0xffffffffu, S.norder, 0), cu = __shfl_sync(0xffffffffu, S.cursor, 0);
+				const uint32_t e1 = nf > WB ? nf - WB : 0u;
+				if(e1 > e0) for(uint32_t id = e0 + lane; id < e1; id += 32) { const uint2 l = ((const uint2 *)(crt_smem + oB))[id & rg.RM]; io.eb[id] = EdgeB{l.x, l.y}; }
+				const uint32_t q1 = no > QW ? no - QW : 0u;
+				if(q1 > q0) for(uint32_t i = max(q0, cu) + lane; i < q1; i += 32) io.order[i] = ((const uint32_t *)(crt_smem + oQ))[i & rg.QM];
+				__syncwarp();
+				if(lane == 0) { if(e1 > e0) S.eflush = e1; if(q1 > q0) S.qflush = q1; }
+				if(rc != 0) break;
+			}
+			if(lane == 0) { st_vol_shared(&ctl[5], (uint32_t)rc); __threadfence_block(); st_vol_shared(&ctl[2], 1u); }
+		} else {
+			// ------------------------------------------------ follower ----------------------------------------------
+			FollowState F;
+			follow_init(F);
+			int splitbits;
+			asm volatile("mov.u32 %0, %1;" : "=r"(splitbits) : "r"(ilog2_u32(io.nvert) + 1));
+			int rc = 0;
+			for(;;) {
+				uint32_t head = 0, done = 0;
+				if(lane == 0) {
+					uint32_t spins = 0;
+					for(;;) {
+						done = ld_vol_shared(&ctl[2]);
+						head = ld_vol_shared(&ctl[0]);
+						if(head != F.tail || done) break;
+						if(++spins > LF_SPIN) { rc = -5; break; }
+						__nanosleep(64);
+					}
+					__threadfence_block();
+					if(rc == 0 && head != F.tail) {
+						const uint32_t upto = min(head, F.tail + (uint32_t)LF_BUDGET);
+						rc = clers_follow(io, rg, F, upto, LF_STAGE, splitbits);
+					}
+				}
+				rc = __shfl_sync(0xffffffffu, rc, 0);
+				head = __shfl_sync(0xffffffffu, head, 0); done = __shfl_sync(0xffffffffu, done, 0);
+				// ---- drains (all lanes) ----
+				const uint32_t f0 = __shfl_sync(0xffffffffu, F.fflush, 0), f1 = __shfl_sync(0xffffffffu, F.nfaces, 0);
+				const uint32_t p0 = __shfl_sync(0xffffffffu, F.pflush, 0), p1 = __shfl_sync(0xffffffffu, F.vcount, 0);
+				const uint32_t a0 = __shfl_sync(0xffffffffu, F.aflush, 0), am = __shfl_sync(0xffffffffu, F.amax, 0);
+				const uint32_t tl = __shfl_sync(0xffffffffu, F.tail, 0);
+				{
+					const uint32_t nw = (f1 - f0)*3u;
+					const uint4 *sf = (const uint4 *)(crt_smem + oF);
+					for(uint32_t k = lane; k < nw; k += 32) {
+						const uint32_t face = f0 + k/3u, comp = k - (k/3u)*3u;
+						const uint32_t v = ((const uint32_t *)(sf + (face & rg.FM)))[comp];
+						const size_t at = (size_t)f0*3u + k;
+						if(io.faces16) io.faces16[at] = (uint16_t)v; else io.faces32[at] = v;
+					}
+					const uint4 *sp = (const uint4 *)(crt_smem + oP);
+					uint4 *dst = (uint4 *)io.pred;
+					for(uint32_t v = p0 + lane; v < p1; v += 32) dst[v] = sp[v & rg.PM];
+				}
+				uint32_t a1 = am > WA ? am - WA : 0u;
+				if(rc == 2) a1 = 0;
+				if(a1 > a0) for(uint32_t id = a0 + lane; id < a1; id += 32) { const uint4 a = ((const uint4 *)(crt_smem + oA))[id & rg.AM]; io.ea[id] = EdgeA{a.x, a.y, a.z, 0}; }
+				__syncwarp();
+				if(lane == 0) {
+					F.fflush = f1; F.pflush = p1;
+					if(rc == 2) { F.nfaces = F.fflush = F.gstart; F.aflush = 0; F.amax = 0; rc = 0; }   // group restart: replay the G word
+					else if(a1 > a0) F.aflush = a1;
+					__threadfence_block();
+					st_vol_shared(&ctl[1], F.tail);
+				}
+				rc = __shfl_sync(0xffffffffu, rc, 0);
+				if(rc < 0) { if(lane == 0) st_vol_shared(&ctl[3], 1u); break; }
+				if(done && head == tl) break;
+			}
+			const uint32_t lead_rc = ld_vol_shared(&ctl[5]);
+			uint32_t vcount = __shfl_sync(0xffffffffu, F.vcount, 0);
+			const bool bad = rc < 0 || (int)lead_rc < 0;
+			if(lane == 0) { if(bad) B.status[mi] = -5; B.vertex_count[mi] = vcount; }
+			uint4 *pred = (uint4 *)M->pred_ptr;
+			if(bad) vcount = 0;
+			for(uint32_t v = vcount + lane; v < M->nvert; v += 32) pred[v] = make_uint4(0, 0, 0, 0);
+		}
+	}
+}
+
+// =========================================================================================================
 // K5  mesh delta inverse.  v[i] += v[a] + v[b] - v[c] (parallelogram) or v[i] += v[a], with a,b,c < i chosen by the
 //     topology: a recurrence on a DAG.  A warp takes 32 consecutive vertices per round, lane = vertex:
 //       1. every lane loads its prediction and residual, and gathers the operands that lie OUTSIDE the block from
@@ -768,18 +946,33 @@ int launch_bit_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 }
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
-	// few meshes: bigger rings (3 CTAs per SM);  many meshes: smaller rings so that more serial chains share an SM
-	uint32_t R = 4096, Q = 2048;
-	if(nwork > (uint32_t)sms*2u) { R = 1024; Q = 1024; }
-	const size_t smem = (size_t)R*24 + (size_t)Q*4 + 2*(size_t)CLERS_STAGE*16;
-	static size_t configured = 0;
-	if(configured < smem) {
-		cudaError_t e = cudaFuncSetAttribute(k_clers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if(e != cudaSuccess) return (int)e;
-		configured = smem;
+	static int mode = -1;                 // CORTO_CLERS=1w selects the single-warp machine (clers_run); default: leader / follower
+	if(mode < 0) { const char *e = getenv("CORTO_CLERS"); mode = (e && e[0] == '1') ? 1 : 2; }
+	const uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
+	if(mode == 1) {
+		uint32_t R = 4096, Q = 2048;
+		if(nwork > (uint32_t)sms*2u) { R = 1024; Q = 1024; }
+		const size_t smem = (size_t)R*24 + (size_t)Q*4 + 2*(size_t)CLERS_STAGE*16;
+		static size_t configured = 0;
+		if(configured < smem) {
+			cudaError_t e = cudaFuncSetAttribute(k_clers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if(e != cudaSuccess) return (int)e;
+			configured = smem;
+		}
+		k_clers<<<g, 32, smem, s>>>(B, order, nwork, scratch, ticket, R, Q);
+	} else {
+		// few meshes: big rings (2 CTAs per SM);  many meshes: small rings so that more serial chains share an SM
+		uint32_t RB = 4096, Q = 2048, RA = 2048;
+		if(nwork > (uint32_t)sms*2u) { RB = 1024; Q = 1024; RA = 1024; }
+		const size_t smem = (size_t)RB*8 + (size_t)Q*4 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
+		static size_t configured = 0;
+		if(configured < smem) {
+			cudaError_t e = cudaFuncSetAttribute(k_clers_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if(e != cudaSuccess) return (int)e;
+			configured = smem;
+		}
+		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, Q, RA);
 	}
-	uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
-	k_clers<<<g, 32, smem, s>>>(B, order, nwork, scratch, ticket, R, Q);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cudaStream_t s) {

@@ -82,6 +82,41 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		}
 		vc = S.vertex_count;
 		rc = rc < 0 ? rc : 0;
+	} else if(ring_q < 0) {
+		// v4 leader / follower (clers_lead + clers_follow) interleaved chunk by chunk; RB = RA = ring_r, Q = -ring_q
+		const uint32_t R = (uint32_t)ring_r, Q = (uint32_t)(-ring_q);
+		const int budget = (int)(std::min(R, Q)/8);
+		uint32_t ST = 1; while(ST < 3u*budget + 8) ST <<= 1;
+		uint32_t LGN = 1; while(LGN < 4u*budget + 16) LGN <<= 1;
+		std::vector<uint4_t> ra(R), sf(ST), sp(ST); std::vector<uint2_t> rb(R); std::vector<uint32_t> rq(Q), lg(LGN);
+		ArrayRings rg{ra.data(), rb.data(), rq.data(), sf.data(), sp.data(), R - 1, Q - 1, ST - 1, ST - 1, lg.data(), LGN - 1, R - 1};
+		const uint32_t W = R - 3u*budget, QW = Q - 3u*budget;
+		const int splitbits = ilog2_u32(io.nvert) + 1;
+		LeadState L; lead_init(L, io);
+		FollowState F; follow_init(F);
+		int lrc = 0; rc = 0;
+		for(int guard = 0; guard < (1 << 30) && rc >= 0; guard++) {
+			lrc = clers_lead(io, rg, L, budget);
+			if(lrc < 0) { rc = lrc; break; }
+			const uint32_t e1 = L.nfront > W ? L.nfront - W : 0;
+			if(e1 > L.eflush) { for(uint32_t id = L.eflush; id < e1; id++) { const uint2_t l = rb[id & (R - 1)]; eb[id] = EdgeB{l.x, l.y}; } L.eflush = e1; }
+			const uint32_t q1 = L.norder > QW ? L.norder - QW : 0;
+			if(q1 > L.qflush) { for(uint32_t i = std::max(L.qflush, L.cursor); i < q1; i++) order[i] = rq[i & (Q - 1)]; L.qflush = q1; }
+			while(F.tail < L.nlog && rc >= 0) {
+				const uint32_t upto = std::min(L.nlog, F.tail + (uint32_t)budget);
+				const int frc = clers_follow(io, rg, F, upto, ST, splitbits);
+				for(uint32_t f = F.fflush; f < F.nfaces; f++) { const uint4_t v = sf[f & (ST - 1)]; faces[(size_t)f*3] = v.x; faces[(size_t)f*3 + 1] = v.y; faces[(size_t)f*3 + 2] = v.z; }
+				for(uint32_t v = F.pflush; v < F.vcount; v++) { const uint4_t x = sp[v & (ST - 1)]; pred[(size_t)v*4] = x.x; pred[(size_t)v*4 + 1] = x.y; pred[(size_t)v*4 + 2] = x.z; pred[(size_t)v*4 + 3] = 0; }
+				F.fflush = F.nfaces; F.pflush = F.vcount;
+				if(frc == 2) { F.nfaces = F.fflush = F.gstart; F.aflush = 0; F.amax = 0; continue; }
+				if(frc < 0) { rc = frc; break; }
+				const uint32_t a1 = F.amax > W ? F.amax - W : 0;
+				if(a1 > F.aflush) { for(uint32_t id = F.aflush; id < a1; id++) { const uint4_t a = ra[id & (R - 1)]; ea[id] = EdgeA{a.x, a.y, a.z, 0}; } F.aflush = a1; }
+			}
+			if(lrc == 1) break;
+		}
+		vc = F.vcount;
+		rc = rc < 0 ? rc : 0;
 	} else rc = -99;
 	for(uint32_t v = 0; v < pm.nvert; v++) for(int k = 0; k < 3; k++) prediction[v*3 + k] = pred[(size_t)v*4 + k];
 	return rc;
