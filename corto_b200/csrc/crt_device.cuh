@@ -244,6 +244,7 @@ struct ClersIO {
 	const uint32_t *group_ends; uint32_t ngroups;
 	uint32_t nvert, nface;
 	EdgeA *ea; EdgeB *eb; uint32_t *order; uint32_t *delayed; uint32_t cap;
+	uint8_t *fl;        // v4: flag byte per edge (global backing of the flag ring); aliases `order`, which v4 does not use
 	uint32_t *faces32; uint16_t *faces16;
 	uint32_t *pred;     // 4 x u32 per vertex
 };
@@ -613,33 +614,41 @@ save:
 // Both are lane-0 machines; the remaining lanes of each warp do the coalesced drains.
 // Log word: type << 28 | id.
 enum { LG_TV = 0, LG_TS = 1, LG_V = 2, LG_S = 3, LG_L = 4, LG_R = 5, LG_E = 6, LG_P = 7, LG_M = 8, LG_G = 9 };
-constexpr uint32_t CLERS_DEL = 0x80000000u;       // `deleted` lives in the top bit of an edge's prev link
-constexpr uint32_t CLERS_NOLINK = 0x7FFFFFFFu;    // placeholder for a link that is still deferred
+constexpr uint32_t CLERS_DEL = 1u;                // flag byte per edge: deleted
+constexpr uint32_t CLERS_NQ = 2u;                 // flag byte per edge: "not queued": the implicit FIFO skips this edge (materialised register edges)
+constexpr uint32_t CLERS_IDMASK = 0x0FFFFFFFu;    // ids fit the 28 payload bits of a log word
+constexpr uint32_t CLERS_NOLINK = 0x0FFFFFFFu;    // placeholder for a link that is still deferred
 
 struct LeadState {
 	uint32_t cler; uint64_t cw, cw_next;
 	uint32_t g, start, end;
-	uint32_t nfront, norder, cursor, ndelayed;
+	uint32_t nfront, scan, ndelayed;   // scan: next edge id the implicit FIFO looks at
 	uint32_t have, lp, ln, cf, cprev, cnext;
-	uint32_t eflush, qflush;
-	uint32_t nlog;
+	uint32_t eflush;
+	uint32_t nlog, bad;
 };
 CRT_HD void lead_init(LeadState &S, const ClersIO &io) {
 	S.cler = 0; S.cw = io.nclers ? load_u64(io.clers) : 0; S.cw_next = io.nclers > 8 ? load_u64(io.clers + 8) : 0;
-	S.g = 0; S.start = S.end = 0; S.nfront = S.norder = S.cursor = S.ndelayed = 0;
-	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.cprev = S.cnext = 0; S.eflush = S.qflush = 0; S.nlog = 0;
+	S.g = 0; S.start = S.end = 0; S.nfront = S.scan = S.ndelayed = 0;
+	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.cprev = S.cnext = 0; S.eflush = 0; S.nlog = 0; S.bad = 0;
 }
 
 CRT_COLD static uint2_t lead_g_load(const EdgeB *eb, uint32_t x) { const EdgeB l = eb[x]; return uint2_t{l.prev, l.next}; }
+CRT_COLD static uint32_t lead_g_flag(const uint8_t *fl, uint32_t x) { return fl[x]; }
+CRT_COLD static void lead_g_set_flag(uint8_t *fl, uint32_t x, uint32_t v) { fl[x] = (uint8_t)v; }
 
-// Link machine.  Consumes at most `budget` symbols (every symbol yields at most 2 log words, a pop 1).  Returns 1 when all
-// groups are done, 0 to be called again after the caller drained / waited for log space, < 0 on a topology error.
+// Link machine.  The reference's faceorder FIFO (decoder.cpp:213-215) holds exactly the queued edges in creation order,
+// and ids here are allocated in creation order too, so the FIFO is IMPLICIT: popping = scanning ids upward for the next
+// edge that is queued and alive (a flag byte per edge: CLERS_DEL / CLERS_NQ).  No queue is stored.
+// Consumes at most `budget` symbols (each yields at most 2 log words, a pop 1).  Returns 1 when all groups are done, 0 to
+// be called again after the caller drained / waited for log space, < 0 on a topology error.  There are no exits from
+// inside the hot paths: errors set a sticky flag and indices are clamped, the flag is reported at the chunk end.
 template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &S, int budget) {
 	uint32_t cler = S.cler, start = S.start, end = S.end;
-	uint32_t nfront = S.nfront, norder = S.norder, cursor = S.cursor, ndel = S.ndelayed, nlog = S.nlog;
+	uint32_t nfront = S.nfront, scan = S.scan, ndel = S.ndelayed, nlog = S.nlog, bad = S.bad;
 	uint64_t cw = S.cw, cwn = S.cw_next;
 	uint32_t have = S.have, lp = S.lp, ln = S.ln, f = S.cf, prev = S.cprev, next = S.cnext, g = S.g;
-	const uint32_t eflush = S.eflush, qflush = S.qflush, nclers = io.nclers, cap = io.cap;
+	const uint32_t eflush = S.eflush, nclers = io.nclers, cap = io.cap;
 	uint32_t n = nclers - cler;
 	if(n > (uint32_t)budget) n = (uint32_t)budget;
 	int rc = 0;
@@ -652,11 +661,14 @@ template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &
 #define LD_SET_NEXT(x, v) do { if((x) >= eflush) rg.stB_next(x, v); else clers_g_set_next(io.eb, x, v); } while(0)
 #define LD_SET_PREV(x, v) do { if((x) >= eflush) rg.stB_prev(x, v); else clers_g_set_prev(io.eb, x, v); } while(0)
 #define LD_LOADB(ID_, P_, Q_) do { if((ID_) >= eflush) rg.ldB(ID_, P_, Q_); else { const uint2_t t_ = lead_g_load(io.eb, ID_); P_ = t_.x; Q_ = t_.y; } } while(0)
+#define LD_FLAG(ID_) (((ID_) >= eflush) ? rg.ldFl(ID_) : lead_g_flag(io.fl, ID_))
+#define LD_SET_FLAG(ID_, V_) do { if((ID_) >= eflush) rg.stFl(ID_, V_); else lead_g_set_flag(io.fl, ID_, V_); } while(0)
+// new id, clamped so that a corrupt stream cannot run past the scratch arrays
+#define LD_NEWID(ID_) do { ID_ = nfront; bad |= (nfront >= cap); nfront += (nfront < cap); } while(0)
 #define LD_MATERIALISE()                                                                                 \
 	do {                                                                                                 \
-		if(nfront >= cap) return -5;                                                                     \
-		f = nfront++;                                                                                    \
-		rg.stB(f, prev, next);                                                                           \
+		LD_NEWID(f);                                                                                     \
+		rg.stB(f, prev, next); rg.stFl(f, CLERS_NQ);                                                     \
 		if(lp) LD_SET_NEXT(prev, f);                                                                     \
 		if(ln) LD_SET_PREV(next, f);                                                                     \
 		lp = ln = 0;                                                                                     \
@@ -672,52 +684,45 @@ template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &
 				if(st > io.nface) st = io.nface;
 				g++;
 				start = st; end = e;
-				nfront = norder = cursor = ndel = 0;
+				nfront = scan = ndel = 0;
 				LD_LOG(LG_G, g - 1);
-				if(eflush | qflush) { S.eflush = 0; S.qflush = 0; rc = 0; break; }   // rings restart: reset the flushed limits first
+				if(eflush) { S.eflush = 0; rc = 0; break; }   // ring restarts: reset the flushed limit first
 				continue;
 			}
-			uint32_t dead = 1, p = 0, q = 0;
-			while(cursor < norder) {                   // FIFO, skipping edges deleted since they were queued
-				f = (cursor >= qflush) ? rg.ldQ(cursor) : io.order[cursor];
-				cursor++;
-				LD_LOADB(f, p, q);
-				dead = p & CLERS_DEL;
-				if(!dead) break;
+			uint32_t skip = 1;
+			while(scan < nfront) {                     // implicit FIFO: next queued, alive edge in id order
+				f = scan++;
+				skip = LD_FLAG(f);
+				if(!skip) break;
 			}
-			if(dead && ndel) {
+			if(skip && ndel) {
 				f = io.delayed[--ndel];
-				LD_LOADB(f, p, q);
-				dead = p & CLERS_DEL;
-				if(dead) continue;
+				skip = LD_FLAG(f) & CLERS_DEL;
+				if(skip) continue;
 			}
-			if(!dead) { prev = p; next = q; lp = ln = 0; have = 1; LD_LOG(LG_P, f); }
+			if(!skip) { LD_LOADB(f, prev, next); lp = ln = 0; have = 1; LD_LOG(LG_P, f); }
 			else {                                     // nothing pending: start triangle
-				if(n == 0) { rc = (cler >= nclers) ? -5 : 0; break; }
+				if(n == 0) break;
 				n--;
-				if(nfront + 3 > cap) return -5;
-				uint32_t c;
+				uint32_t c, b;
 				LD_FETCH(c);
-				const uint32_t b = nfront;
+				b = nfront; bad |= (nfront + 3 > cap); nfront += (nfront + 3 <= cap) ? 3u : 0u;
 				rg.stB(b, b + 2, b + 1); rg.stB(b + 1, b + 0, b + 2); rg.stB(b + 2, b + 1, b + 0);
-				rg.stQ(norder, b); rg.stQ(norder + 1, b + 1); rg.stQ(norder + 2, b + 2);
-				norder += 3; nfront += 3;
+				rg.stFl(b, 0); rg.stFl(b + 1, 0); rg.stFl(b + 2, 0);
 				LD_LOG(c == C_SPLIT ? LG_TS : LG_TV, b);
 				start += 1;
 				continue;
 			}
 		}
-		do {
-			if(n == 0) { rc = (cler >= nclers) ? -5 : 0; goto save; }
+		while(n) {
 			n--;
 			uint32_t c;
 			LD_FETCH(c);
 			if(c == C_VERTEX || c == C_SPLIT) {
-				if(nfront >= cap) return -5;
-				const uint32_t b = nfront++;
-				rg.stB(b, CLERS_NOLINK, next);             // second new edge: persistent, queued; its prev link is deferred
+				uint32_t b;
+				LD_NEWID(b);
+				rg.stB(b, CLERS_NOLINK, next); rg.stFl(b, 0);   // second new edge: persistent, queued; its prev link is deferred
 				LD_SET_PREV(next, b);
-				rg.stQ(norder, b); norder++;
 				LD_LOG(c == C_VERTEX ? LG_V : LG_S, b);
 				start++;
 				next = b; lp = 1; ln = 1; f = CLERS_NOID;
@@ -726,51 +731,55 @@ template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &
 				uint32_t pp, pn;
 				LD_LOADB(prev, pp, pn);
 				(void)pn;
-				LD_SET_PREV(prev, pp | CLERS_DEL);
+				LD_SET_FLAG(prev, CLERS_DEL);
 				LD_LOG(LG_L, prev);
 				start++;
-				prev = pp & ~CLERS_DEL; lp = 1; ln = 1; f = CLERS_NOID;
+				prev = pp; lp = 1; ln = 1; f = CLERS_NOID;
 			} else if(c == C_RIGHT) {
 				if((lp | ln) && prev == next) LD_MATERIALISE();
 				uint32_t np, nn;
 				LD_LOADB(next, np, nn);
-				LD_SET_PREV(next, np | CLERS_DEL);
+				(void)np;
+				LD_SET_FLAG(next, CLERS_DEL);
 				LD_LOG(LG_R, next);
 				start++;
 				next = nn; lp = 1; ln = 1; f = CLERS_NOID;
-			} else if(c == C_BOUNDARY) {
-				if(f == CLERS_NOID) LD_MATERIALISE();
-				have = 0; break;
-			} else if(c == C_DELAY) {
-				if(f == CLERS_NOID) LD_MATERIALISE();
-				io.delayed[ndel++] = f;
-				have = 0; break;
 			} else if(c == C_END) {
 				if((lp | ln) && prev == next) LD_MATERIALISE();
 				uint32_t pp, pn, np, nn;
 				LD_LOADB(prev, pp, pn);
 				LD_LOADB(next, np, nn);
 				(void)pn;
-				LD_SET_PREV(prev, pp | CLERS_DEL);
-				LD_SET_PREV(next, np | CLERS_DEL);
-				LD_SET_NEXT(pp & ~CLERS_DEL, nn);
-				LD_SET_PREV(nn, pp & ~CLERS_DEL);
+				(void)np;
+				LD_SET_FLAG(prev, CLERS_DEL);
+				LD_SET_FLAG(next, CLERS_DEL);
+				LD_SET_NEXT(pp, nn);
+				LD_SET_PREV(nn, pp);
 				LD_LOG(LG_E, prev);
 				start++;
 				have = 0; break;
-			} else return -5;
-		} while(start < end);
-		have = 0;
+			} else {                                       // BOUNDARY, DELAY (anything else is a corrupt stream: treated as BOUNDARY + flag)
+				bad |= (c != C_BOUNDARY && c != C_DELAY);
+				if(f == CLERS_NOID) LD_MATERIALISE();
+				if(c == C_DELAY) io.delayed[ndel++] = f;
+				have = 0; break;
+			}
+			if(start >= end) { have = 0; break; }
+		}
+		if(have) break;                                    // budget used up in the middle of a strip
 	}
-save:
-	S.cler = cler; S.start = start; S.end = end; S.nfront = nfront; S.norder = norder; S.cursor = cursor; S.ndelayed = ndel;
-	S.cw = cw; S.cw_next = cwn; S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.cprev = prev; S.cnext = next; S.g = g; S.nlog = nlog;
+	if(rc == 0 && (bad || (cler >= nclers && !(start >= end && g >= io.ngroups)))) rc = -5;   // flagged, or the stream ran dry with faces missing
+	S.cler = cler; S.start = start; S.end = end; S.nfront = nfront; S.scan = scan; S.ndelayed = ndel;
+	S.cw = cw; S.cw_next = cwn; S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.cprev = prev; S.cnext = next; S.g = g; S.nlog = nlog; S.bad = bad;
 	return rc;
 #undef LD_FETCH
 #undef LD_LOG
 #undef LD_SET_NEXT
 #undef LD_SET_PREV
 #undef LD_LOADB
+#undef LD_FLAG
+#undef LD_SET_FLAG
+#undef LD_NEWID
 #undef LD_MATERIALISE
 }
 
@@ -890,6 +899,9 @@ struct ArrayRings {
 	CRT_HD void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c) { ra[id & AM] = uint4_t{a, b, c, 0}; }
 	CRT_HD void stLog(uint32_t i, uint32_t w) { lg[i & LM] = w; }
 	CRT_HD uint32_t ldLog(uint32_t i) const { return lg[i & LM]; }
+	uint8_t *rf;
+	CRT_HD uint32_t ldFl(uint32_t id) const { return rf[id & RM]; }
+	CRT_HD void stFl(uint32_t id, uint32_t v) { rf[id & RM] = (uint8_t)v; }
 };
 
 }  // namespace crtb

@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(32) k_clers(DevBatch B, const uint32_t *mesh_o
 //      share global state.  Every spin is bounded; a stuck partner turns into CRT_E_TOPOLOGY, not a hang.
 // =========================================================================================================
 struct SmemRings4 {
-	uint32_t aB, aQ, aL, aA, aF, aP;      // shared-space byte addresses
-	uint32_t RM, QM, LM, AM, FM, PM;
+	uint32_t aB, aX, aL, aA, aF, aP;      // shared-space byte addresses: links, flags, log, labels, staged faces / predictions
+	uint32_t RM, LM, AM, FM, PM;
 	__device__ __forceinline__ void ldB(uint32_t id, uint32_t &p, uint32_t &n) const {
 		asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(p), "=r"(n) : "r"(aB + ((id & RM) << 3)));
 	}
@@ -415,8 +415,8 @@ struct SmemRings4 {
 	}
 	__device__ __forceinline__ void stB_prev(uint32_t id, uint32_t p) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3)), "r"(p) : "memory"); }
 	__device__ __forceinline__ void stB_next(uint32_t id, uint32_t n) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3) + 4u), "r"(n) : "memory"); }
-	__device__ __forceinline__ uint32_t ldQ(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aQ + ((i & QM) << 2))); return v; }
-	__device__ __forceinline__ void stQ(uint32_t i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aQ + ((i & QM) << 2)), "r"(v) : "memory"); }
+	__device__ __forceinline__ uint32_t ldFl(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aX + (id & RM))); return v; }
+	__device__ __forceinline__ void stFl(uint32_t id, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(aX + (id & RM)), "r"(v) : "memory"); }
 	__device__ __forceinline__ void stLog(uint32_t i, uint32_t w) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aL + ((i & LM) << 2)), "r"(w) : "memory"); }
 	__device__ __forceinline__ uint32_t ldLog(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aL + ((i & LM) << 2))); return v; }
 	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const {
@@ -442,16 +442,16 @@ constexpr uint32_t LF_LOG = 1024;       // log ring words
 constexpr uint32_t LF_SPIN = 1u << 26;  // bound on every wait loop
 
 __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
-                                                  uint32_t RB, uint32_t Q, uint32_t RA) {
+                                                  uint32_t RB, uint32_t RA) {
 	__shared__ uint32_t ctl[8];          // 0 head, 1 tail, 2 done, 3 abort, 4 mesh, 5 lead rc
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	SmemRings4 rg;
-	const uint32_t oB = 0, oQ = oB + RB*8u, oL = oQ + Q*4u, oA = oL + LF_LOG*4u, oF = oA + RA*16u, oP = oF + LF_STAGE*16u;
+	const uint32_t oB = 0, oX = oB + RB*8u, oL = oX + RB, oA = oL + LF_LOG*4u, oF = oA + RA*16u, oP = oF + LF_STAGE*16u;
 	uint32_t sbase;
 	asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(crt_smem)));
-	rg.aB = sbase + oB; rg.aQ = sbase + oQ; rg.aL = sbase + oL; rg.aA = sbase + oA; rg.aF = sbase + oF; rg.aP = sbase + oP;
-	rg.RM = RB - 1; rg.QM = Q - 1; rg.LM = LF_LOG - 1; rg.AM = RA - 1; rg.FM = LF_STAGE - 1; rg.PM = LF_STAGE - 1;
-	const uint32_t WB = RB - 3u*LF_BUDGET, QW = Q - 3u*LF_BUDGET, WA = RA - 3u*LF_BUDGET;
+	rg.aB = sbase + oB; rg.aX = sbase + oX; rg.aL = sbase + oL; rg.aA = sbase + oA; rg.aF = sbase + oF; rg.aP = sbase + oP;
+	rg.RM = RB - 1; rg.LM = LF_LOG - 1; rg.AM = RA - 1; rg.FM = LF_STAGE - 1; rg.PM = LF_STAGE - 1;
+	const uint32_t WB = RB - 3u*LF_BUDGET, WA = RA - 3u*LF_BUDGET;
 	for(;;) {
 		__syncthreads();
 		if(threadIdx.x == 0) { ctl[4] = atomicAdd(ticket, 1u); ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; ctl[3] = 0; ctl[5] = 0; }
@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 		io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
 		io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
 		io.pred = (uint32_t *)M->pred_ptr;
+		io.fl = (uint8_t *)io.order;           // v4 stores no FIFO: the `order` scratch backs the flag ring
 		if(warp == 0) {
 			// ------------------------------------------------ leader ------------------------------------------------
 			LeadState S;
@@ -493,13 +494,13 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 				}
 				rc = __shfl_sync(0xffffffffu, rc, 0);
 				const uint32_t e0 = __shfl_sync(0xffffffffu, S.eflush, 0), nf = __shfl_sync(0xffffffffu, S.nfront, 0);
-				const uint32_t q0 = __shfl_sync(0xffffffffu, S.qflush, 0), no = __shfl_sync(0xffffffffu, S.norder, 0), cu = __shfl_sync(0xffffffffu, S.cursor, 0);
 				const uint32_t e1 = nf > WB ? nf - WB : 0u;
-				if(e1 > e0) for(uint32_t id = e0 + lane; id < e1; id += 32) { const uint2 l = ((const uint2 *)(crt_smem + oB))[id & rg.RM]; io.eb[id] = EdgeB{l.x, l.y}; }
-				const uint32_t q1 = no > QW ? no - QW : 0u;
-				if(q1 > q0) for(uint32_t i = max(q0, cu) + lane; i < q1; i += 32) io.order[i] = ((const uint32_t *)(crt_smem + oQ))[i & rg.QM];
+				if(e1 > e0) for(uint32_t id = e0 + lane; id < e1; id += 32) {
+					const uint2 l = ((const uint2 *)(crt_smem + oB))[id & rg.RM];
+					io.eb[id] = EdgeB{l.x, l.y}; io.fl[id] = (crt_smem + oX)[id & rg.RM];
+				}
 				__syncwarp();
-				if(lane == 0) { if(e1 > e0) S.eflush = e1; if(q1 > q0) S.qflush = q1; }
+				if(lane == 0 && e1 > e0) S.eflush = e1;
 				if(rc != 0) break;
 			}
 			if(lane == 0) { st_vol_shared(&ctl[5], (uint32_t)rc); __threadfence_block(); st_vol_shared(&ctl[2], 1u); }
@@ -962,16 +963,16 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 		k_clers<<<g, 32, smem, s>>>(B, order, nwork, scratch, ticket, R, Q);
 	} else {
 		// few meshes: big rings (2 CTAs per SM);  many meshes: small rings so that more serial chains share an SM
-		uint32_t RB = 4096, Q = 2048, RA = 2048;
-		if(nwork > (uint32_t)sms*2u) { RB = 1024; Q = 1024; RA = 1024; }
-		const size_t smem = (size_t)RB*8 + (size_t)Q*4 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
+		uint32_t RB = 4096, RA = 2048;
+		if(nwork > (uint32_t)sms*2u) { RB = 1024; RA = 1024; }
+		const size_t smem = (size_t)RB*9 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
 		static size_t configured = 0;
 		if(configured < smem) {
 			cudaError_t e = cudaFuncSetAttribute(k_clers_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if(e != cudaSuccess) return (int)e;
 			configured = smem;
 		}
-		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, Q, RA);
+		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, RA);
 	}
 	LAUNCH_CHECK(); return 0;
 }

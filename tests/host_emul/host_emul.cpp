@@ -51,6 +51,7 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 	uint32_t cap = 3*maxg + 16;
 	std::vector<EdgeA> ea(cap); std::vector<EdgeB> eb(cap); std::vector<uint32_t> order(cap), delayed(cap), pred((size_t)pm.nvert*4 + 4);
 	ClersIO io;
+	io.fl = nullptr;
 	io.clers = clers; io.nclers = nclers;
 	io.split = (const uint32_t *)(blob + pm.split_off); io.split_nwords = pm.split_nwords;
 	io.group_ends = pm.group_ends.data(); io.ngroups = (uint32_t)pm.group_ends.size();
@@ -89,8 +90,10 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		uint32_t ST = 1; while(ST < 3u*budget + 8) ST <<= 1;
 		uint32_t LGN = 1; while(LGN < 4u*budget + 16) LGN <<= 1;
 		std::vector<uint4_t> ra(R), sf(ST), sp(ST); std::vector<uint2_t> rb(R); std::vector<uint32_t> rq(Q), lg(LGN);
-		ArrayRings rg{ra.data(), rb.data(), rq.data(), sf.data(), sp.data(), R - 1, Q - 1, ST - 1, ST - 1, lg.data(), LGN - 1, R - 1};
-		const uint32_t W = R - 3u*budget, QW = Q - 3u*budget;
+		std::vector<uint8_t> rf(R);
+		ArrayRings rg{ra.data(), rb.data(), rq.data(), sf.data(), sp.data(), R - 1, Q - 1, ST - 1, ST - 1, lg.data(), LGN - 1, R - 1, rf.data()};
+		io.fl = (uint8_t *)order.data();
+		const uint32_t W = R - 3u*budget;
 		const int splitbits = ilog2_u32(io.nvert) + 1;
 		LeadState L; lead_init(L, io);
 		FollowState F; follow_init(F);
@@ -99,9 +102,7 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 			lrc = clers_lead(io, rg, L, budget);
 			if(lrc < 0) { rc = lrc; break; }
 			const uint32_t e1 = L.nfront > W ? L.nfront - W : 0;
-			if(e1 > L.eflush) { for(uint32_t id = L.eflush; id < e1; id++) { const uint2_t l = rb[id & (R - 1)]; eb[id] = EdgeB{l.x, l.y}; } L.eflush = e1; }
-			const uint32_t q1 = L.norder > QW ? L.norder - QW : 0;
-			if(q1 > L.qflush) { for(uint32_t i = std::max(L.qflush, L.cursor); i < q1; i++) order[i] = rq[i & (Q - 1)]; L.qflush = q1; }
+			if(e1 > L.eflush) { for(uint32_t id = L.eflush; id < e1; id++) { const uint2_t l = rb[id & (R - 1)]; eb[id] = EdgeB{l.x, l.y}; io.fl[id] = rf[id & (R - 1)]; } L.eflush = e1; }
 			while(F.tail < L.nlog && rc >= 0) {
 				const uint32_t upto = std::min(L.nlog, F.tail + (uint32_t)budget);
 				const int frc = clers_follow(io, rg, F, upto, ST, splitbits);
