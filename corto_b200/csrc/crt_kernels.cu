@@ -587,20 +587,32 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 // =========================================================================================================
 template <typename T, int NC>
 __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint32_t nvert, bool par, int lane) {
+	// software pipeline: the NEXT round's prediction and residuals are fetched while this round computes (they are not
+	// touched by this round), so each round pays one dependent memory round trip (the operand gather) instead of two
+	uint4 p_next = (uint32_t)lane < nvert ? pred[lane] : make_uint4(0, 0, 0, 0);
+	uint32_t x_next[NC];
+#pragma unroll
+	for(int k = 0; k < NC; k++) x_next[k] = (uint32_t)lane < nvert ? (uint32_t)v[(size_t)lane*NC + k] : 0u;
 	for(uint32_t base = 0; base < nvert; base += 32) {
 		const uint32_t i = base + lane;
 		const bool in = i < nvert;
 		const bool act = in && i > 0;                 // vertex 0 keeps its residual (loops start at 1)
-		uint4 p = in ? pred[i] : make_uint4(0, 0, 0, 0);
+		const uint4 p = p_next;
 		const uint32_t a = p.x, b = p.y, c = p.z;
 		uint32_t x[NC], fa[NC], fb[NC], fc[NC];
 		const bool a_in = act && (a - base) < 32u, b_in = act && par && (b - base) < 32u, c_in = act && par && (c - base) < 32u;
 #pragma unroll
 		for(int k = 0; k < NC; k++) {
-			x[k] = in ? (uint32_t)v[(size_t)i*NC + k] : 0u;
+			x[k] = x_next[k];
 			fa[k] = (act && !a_in && a < nvert) ? (uint32_t)v[(size_t)a*NC + k] : 0u;
 			fb[k] = (act && par && !b_in && b < nvert) ? (uint32_t)v[(size_t)b*NC + k] : 0u;
 			fc[k] = (act && par && !c_in && c < nvert) ? (uint32_t)v[(size_t)c*NC + k] : 0u;
+		}
+		{
+			const uint32_t in2 = i + 32;
+			p_next = in2 < nvert ? pred[in2] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+			for(int k = 0; k < NC; k++) x_next[k] = in2 < nvert ? (uint32_t)v[(size_t)in2*NC + k] : 0u;
 		}
 		// pure chain: every in-block operand is "a = previous lane"
 		const bool chain_ok = !act || (!b_in && !c_in && (!a_in || a == i - 1));
@@ -609,9 +621,7 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 			for(int k = 0; k < NC; k++) {
 				// r = everything except the in-block a term; lanes whose a is outside (or inactive) start a new segment
 				uint32_t r = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k];
-				const bool head = !a_in;                   // segment head: does not add the previous lane
-				// segmented inclusive scan: value + flag
-				uint32_t val = r; bool flag = head;
+				uint32_t val = r; bool flag = !a_in;       // segmented inclusive scan: value + "segment head" flag
 #pragma unroll
 				for(int d = 1; d < 32; d <<= 1) {
 					const uint32_t ov = __shfl_up_sync(0xffffffffu, val, d);
