@@ -1,0 +1,51 @@
+"""The C++ facade (include/corto_b200/decoder.h) keeps the reference's crt::Decoder source API: a program written like the
+reference README (tests/cpp/facade_main.cpp) compiles unchanged with -std=c++11 and, on a GPU, reproduces the golden
+arrays; without a GPU it fails with a thrown `const char *`, never a CPU fallback."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import corto_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("facade") / "facade_main")
+    lib = os.path.join(ROOT, "corto_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "facade_main.cpp"), "-L" + lib, "-lcorto_b200", "-Wl,-rpath," + lib, "-o", out])
+    return out
+
+
+def test_facade_compiles_and_fails_loudly_without_gpu(exe, tmp_path):
+    if corto_b200.device_available():
+        pytest.skip("a GPU is visible here")
+    r = subprocess.run([exe, os.path.join(GOLDEN, "grid_est.crt"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["grid_est", "groups3", "torus", "cloud_all", "grid_border"])
+def test_facade_matches_golden(exe, tmp_path, name):
+    out = tmp_path / "o.bin"
+    r = subprocess.run([exe, os.path.join(GOLDEN, name + ".crt"), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = np.fromfile(out, dtype=np.uint8)
+    nv, nf, hn, hc, hu, ng = raw[:24].view(np.uint32)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    pos = 24
+    def take(n, dt):
+        nonlocal pos
+        a = raw[pos:pos + n * np.dtype(dt).itemsize].view(dt); pos += n * np.dtype(dt).itemsize
+        return a
+    assert np.array_equal(take(nv * 3, np.uint32), gold["default/position"].reshape(-1).view(np.uint32))
+    if hn: assert np.array_equal(take(nv * 3, np.uint32), gold["default/normal"].reshape(-1).view(np.uint32))
+    if hc: assert np.array_equal(take(nv * 4, np.uint8), gold["color_out4/color"].reshape(-1))
+    if hu: assert np.array_equal(take(nv * 2, np.uint32), gold["default/uv"].reshape(-1).view(np.uint32))
+    if nf: assert np.array_equal(take(nf * 3, np.uint32), gold["default/index"].reshape(-1))
+    assert ng >= (1 if nf else 0)      # point clouds carry no group unless the encoder added one
