@@ -641,9 +641,10 @@ CRT_COLD static void lead_g_set_flag(uint8_t *fl, uint32_t x, uint32_t v) { fl[x
 // and ids here are allocated in creation order too, so the FIFO is IMPLICIT: popping = scanning ids upward for the next
 // edge that is queued and alive (a flag byte per edge: CLERS_DEL / CLERS_NQ).  No queue is stored.
 // Consumes at most `budget` symbols (each yields at most 2 log words, a pop 1).  Returns 1 when all groups are done, 0 to
-// be called again after the caller drained / waited for log space, < 0 on a topology error.  There are no exits from
+// be called again after the caller drained / waited for log space, 3 (only with vec) when a VERTEX/LEFT run starts and the
+// caller should run its warp-wide window step, < 0 on a topology error.  There are no exits from
 // inside the hot paths: errors set a sticky flag and indices are clamped, the flag is reported at the chunk end.
-template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &S, int budget) {
+template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &S, int budget, bool vec = false) {
 	uint32_t cler = S.cler, start = S.start, end = S.end;
 	uint32_t nfront = S.nfront, scan = S.scan, ndel = S.ndelayed, nlog = S.nlog, bad = S.bad;
 	uint64_t cw = S.cw, cwn = S.cw_next;
@@ -715,6 +716,8 @@ template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &
 			}
 		}
 		while(n) {
+			// a run of VERTEX / LEFT symbols ahead: yield to the caller's warp-wide window step (k_clers_lf: lead_vector)
+			if(vec && n >= 2 && (cler & 7u) <= 6u && ((uint32_t)cw & 0xfefeu) == 0 && end - start >= 2) { rc = 3; break; }
 			n--;
 			uint32_t c;
 			LD_FETCH(c);
@@ -799,15 +802,20 @@ CRT_COLD static uint4_t follow_g_load(const EdgeA *ea, uint32_t x) { const EdgeA
 
 // Label machine: replays log words [S.tail, upto).  Stops early (returns 0 with S.tail < upto) when a staging ring is
 // full (`room` entries left at call time) so the caller can drain; returns 0 normally, < 0 on an inconsistent stream.
-template <class RG> CRT_HD int clers_follow(const ClersIO &io, RG &rg, FollowState &S, uint32_t upto, uint32_t room, int splitbits) {
+template <class RG> CRT_HD int clers_follow(const ClersIO &io, RG &rg, FollowState &S, uint32_t upto, uint32_t room, int splitbits, bool vec = false) {
 	uint32_t v0 = S.v0, v1 = S.v1, v2 = S.v2, vcount = S.vcount, nf = S.nfaces, tail = S.tail, amax = S.amax;
 	uint64_t splitpos = S.splitpos;
 	const uint32_t aflush = S.aflush, nvert = io.nvert, nface = io.nface;
 	int rc = 0;
 #define FW_LOADA(ID_, A_, B_, C_) do { if((ID_) >= aflush) rg.ldA(ID_, A_, B_, C_); else { const uint4_t t_ = follow_g_load(io.ea, ID_); A_ = t_.x; B_ = t_.y; C_ = t_.z; } } while(0)
 	while(tail < upto && room >= 3) {
-		const uint32_t w = rg.ldLog(tail); tail++;
+		const uint32_t w = rg.ldLog(tail);
 		const uint32_t t = w >> 28, id = w & 0x0FFFFFFFu;
+		if(vec && (t == LG_V || t == LG_L) && tail + 1 < upto) {     // two VERTEX/LEFT words in a row: yield to the warp-wide window step
+			const uint32_t t2 = rg.ldLog(tail + 1) >> 28;
+			if(t2 == LG_V || t2 == LG_L) { rc = 3; break; }
+		}
+		tail++;
 		if(t == LG_V || t == LG_S) {
 			uint32_t opp;
 			if(t == LG_V) {

@@ -436,14 +436,140 @@ struct SmemRings4 {
 __device__ __forceinline__ uint32_t ld_vol_shared(const uint32_t *p) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v; }
 __device__ __forceinline__ void st_vol_shared(uint32_t *p, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory"); }
 
+// ---- warp-wide window steps -------------------------------------------------------------------------------------------
+// A run of VERTEX / LEFT symbols is a closed form for the link machine: VERTEX k pushes new id nfront+k (its links are
+// its neighbours in the run), LEFT k consumes the k-th edge of the prev chain.  Only the prev-chain walk is serial (one
+// dependent shared-memory load per LEFT); ids, link records, flags and log words are written by 32 lanes at once.  The
+// scalar machine yields (return 3) when it sees such a run and takes over again at the first other symbol.
+// Returns the number of symbols consumed (>= 2) or 0 when the window must go through the scalar path (loop closure in
+// sight, capacity edge, run too short).  S is valid in lane 0 only.
+__device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S, uint32_t left, uint32_t *chain, uint32_t lane) {
+	const uint32_t FULL = 0xffffffffu;
+	__syncwarp();                                          // lane 0's scalar ring stores are visible to every lane from here
+	const uint32_t cler = __shfl_sync(FULL, S.cler, 0), start = __shfl_sync(FULL, S.start, 0), end = __shfl_sync(FULL, S.end, 0);
+	const uint32_t nfront0 = __shfl_sync(FULL, S.nfront, 0), next0 = __shfl_sync(FULL, S.cnext, 0), nlog0 = __shfl_sync(FULL, S.nlog, 0);
+	const uint32_t eflush = __shfl_sync(FULL, S.eflush, 0);
+	uint32_t lim = min(min(32u, left), min(io.nclers - cler, end - start));
+	const uint32_t sym = lane < lim ? (uint32_t)io.clers[cler + lane] : 0xffu;
+	const bool isV = sym == C_VERTEX, isL = sym == C_LEFT;
+	const uint32_t stop = __ballot_sync(FULL, !(isV || isL));
+	const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+	if(m < 2) return 0;
+	const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
+	const uint32_t Vm = __ballot_sync(FULL, isV) & pm, Lm = __ballot_sync(FULL, isL) & pm;
+	const uint32_t nV = __popc(Vm), nL = __popc(Lm);
+	uint32_t ok = 1;
+	if(lane == 0) {
+		uint32_t p = S.cprev;
+		if(nfront0 + nV > io.cap) ok = 0;
+		for(uint32_t k = 0; k < nL; k++) {                 // the serial part: walk the prev chain
+			chain[k] = p;
+			if(p == next0) ok = 0;                         // the walk wraps around to the right-hand neighbour (small loop): its links
+			                                               // change inside this window, so take the scalar path
+			uint32_t pp, pn;
+			if(p >= eflush) rg.ldB(p, pp, pn); else { const uint2_t t_ = lead_g_load(io.eb, p); pp = t_.x; pn = t_.y; }
+			(void)pn;
+			p = pp;
+		}
+		chain[nL] = p;
+	}
+	__syncwarp();
+	ok = __shfl_sync(FULL, ok, 0);
+	if(!ok) return 0;
+	if(lane < m) {
+		const uint32_t below = (1u << lane) - 1u;
+		if(isV) {
+			const uint32_t r = __popc(Vm & below), b = nfront0 + r;
+			rg.stB(b, r + 1 < nV ? b + 1 : CLERS_NOLINK, r ? b - 1 : next0);
+			rg.stFl(b, 0);
+			rg.stLog(nlog0 + lane, ((uint32_t)LG_V << 28) | b);
+		} else {
+			const uint32_t p = chain[__popc(Lm & below)];
+			if(p >= eflush) rg.stFl(p, CLERS_DEL); else lead_g_set_flag(io.fl, p, CLERS_DEL);
+			rg.stLog(nlog0 + lane, ((uint32_t)LG_L << 28) | p);
+		}
+	}
+	if(lane == 0) {
+		if(nV) { if(next0 >= eflush) rg.stB_prev(next0, nfront0); else clers_g_set_prev(io.eb, next0, nfront0); }
+		S.nfront = nfront0 + nV;
+		S.cprev = chain[nL];
+		if(nV) S.cnext = nfront0 + nV - 1;
+		S.lp = S.ln = 1; S.cf = CLERS_NOID;
+		S.nlog = nlog0 + m; S.start = start + m;
+		const uint32_t c = cler + m, g8 = c & ~7u;          // re-prime the 8-byte symbol window
+		S.cler = c;
+		S.cw = c < io.nclers ? load_u64(io.clers + g8) >> (8u*(c & 7u)) : 0;
+		S.cw_next = g8 + 8 < io.nclers ? load_u64(io.clers + g8 + 8) : 0;
+		if(S.start >= S.end) S.have = 0;
+	}
+	__syncwarp();
+	return m;
+}
+
+// Label machine over a run of VERTEX / LEFT log words: "who defined v0 / v1 last" is a bit trick on the ballot masks,
+// label loads of the LEFTs go out in parallel, faces / predictions / labels are staged by 32 lanes at once.
+__device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState &F, uint32_t upto, uint32_t lane) {
+	const uint32_t FULL = 0xffffffffu;
+	__syncwarp();
+	const uint32_t tail = __shfl_sync(FULL, F.tail, 0);
+	const uint32_t lim = min(32u, upto - tail);
+	const uint32_t w = lane < lim ? rg.ldLog(tail + lane) : 0xffffffffu;
+	const uint32_t t = w >> 28, id = w & 0x0FFFFFFFu;
+	const bool isV = t == LG_V, isL = t == LG_L;
+	uint32_t stop = __ballot_sync(FULL, !(isV || isL));
+	// a LEFT may consume an edge that a VERTEX of this very window creates (the prev chain wrapped around a small loop): its
+	// label does not exist yet, so the window ends in front of it.  Ids grow with creation order: compare with the first V's.
+	const uint32_t vall = __ballot_sync(FULL, isV);
+	const uint32_t firstid = __shfl_sync(FULL, id, vall ? __ffs(vall) - 1 : 0);
+	stop |= __ballot_sync(FULL, isL && vall && id >= firstid && (uint32_t)(__ffs(vall) - 1) < lane);
+	const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+	if(m < 2) return 0;
+	const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
+	const uint32_t Vm = vall & pm, Lm = __ballot_sync(FULL, isL) & pm;
+	const uint32_t nV = __popc(Vm);
+	const uint32_t vcount0 = __shfl_sync(FULL, F.vcount, 0), nf0 = __shfl_sync(FULL, F.nfaces, 0), aflush = __shfl_sync(FULL, F.aflush, 0);
+	const uint32_t v0i = __shfl_sync(FULL, F.v0, 0), v1i = __shfl_sync(FULL, F.v1, 0), v2i = __shfl_sync(FULL, F.v2, 0);
+	if(vcount0 + nV > io.nvert || nf0 + m > io.nface) return 0;     // let the scalar machine flag the error
+	uint32_t a = 0;
+	if(lane < m && isL) {
+		uint32_t t1, t2;
+		if(id >= aflush) rg.ldA(id, a, t1, t2); else { const uint4_t g_ = follow_g_load(io.ea, id); a = g_.x; }
+	}
+	const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
+	const uint32_t x = vcount0 + __popc(Vm & lt);
+	const uint32_t lLE = Lm & le, lLT = Lm & lt, vLE = Vm & le, vLT = Vm & lt;
+	const uint32_t a_le = __shfl_sync(FULL, a, lLE ? 31 - __clz(lLE) : 0), a_lt = __shfl_sync(FULL, a, lLT ? 31 - __clz(lLT) : 0);
+	const uint32_t x_le = __shfl_sync(FULL, x, vLE ? 31 - __clz(vLE) : 0), x_lt = __shfl_sync(FULL, x, vLT ? 31 - __clz(vLT) : 0);
+	const uint32_t v0_after = lLE ? a_le : v0i, v0_before = lLT ? a_lt : v0i;
+	const uint32_t v1_after = vLE ? x_le : v1i, v1_before = vLT ? x_lt : v1i;
+	const uint32_t pv1b = __shfl_up_sync(FULL, v1_before, 1), pv0b = __shfl_up_sync(FULL, v0_before, 1);
+	const uint32_t v2_before = lane == 0 ? v2i : (((Vm >> (lane - 1)) & 1u) ? pv1b : pv0b);
+	if(lane < m) {
+		rg.stF(nf0 + lane, v1_before, v0_before, isV ? x : a);
+		if(isV) { rg.stP(x, v1_before, v0_before, v2_before); rg.stA(id, x, v1_before, v0_before); }
+	}
+	const uint32_t last = m - 1;
+	const uint32_t v0e = __shfl_sync(FULL, v0_after, last), v1e = __shfl_sync(FULL, v1_after, last);
+	const uint32_t v2e = __shfl_sync(FULL, isV ? v1_before : v0_before, last);
+	const uint32_t topid = __shfl_sync(FULL, id, Vm ? 31 - __clz(Vm) : 0);
+	if(lane == 0) {
+		F.v0 = v0e; F.v1 = v1e; F.v2 = v2e;
+		F.vcount = vcount0 + nV; F.nfaces = nf0 + m; F.tail = tail + m;
+		if(nV) F.amax = topid + 1;
+	}
+	__syncwarp();
+	return m;
+}
+
 constexpr int LF_BUDGET = 64;           // symbols per leader chunk / log words per follower batch
 constexpr uint32_t LF_STAGE = 256;      // staged faces / predictions (>= 3*LF_BUDGET)
 constexpr uint32_t LF_LOG = 1024;       // log ring words
 constexpr uint32_t LF_SPIN = 1u << 26;  // bound on every wait loop
 
 __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
-                                                  uint32_t RB, uint32_t RA) {
+                                                  uint32_t RB, uint32_t RA, bool vecmode) {
 	__shared__ uint32_t ctl[8];          // 0 head, 1 tail, 2 done, 3 abort, 4 mesh, 5 lead rc
+	__shared__ uint32_t chain[33];       // prev-chain of a VERTEX/LEFT window (lead_vector)
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	SmemRings4 rg;
 	const uint32_t oB = 0, oX = oB + RB*8u, oL = oX + RB, oA = oL + LF_LOG*4u, oF = oA + RA*16u, oP = oF + LF_STAGE*16u;
@@ -488,11 +614,27 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 						if(ld_vol_shared(&ctl[3]) || ++spins > LF_SPIN) { rc = -5; break; }
 						__nanosleep(64);
 					}
-					if(rc == 0) rc = clers_lead(io, rg, S, LF_BUDGET);
-					__threadfence_block();
-					st_vol_shared(&ctl[0], S.nlog);
 				}
 				rc = __shfl_sync(0xffffffffu, rc, 0);
+				// one chunk: scalar machine, interleaved with warp-wide windows over VERTEX/LEFT runs
+				uint32_t left = LF_BUDGET;
+				while(rc == 0 && left > 0) {
+					uint32_t c0 = 0;
+					if(lane == 0) { c0 = S.cler; rc = clers_lead(io, rg, S, (int)left, vecmode); c0 = S.cler - c0; }
+					rc = __shfl_sync(0xffffffffu, rc, 0);
+					c0 = __shfl_sync(0xffffffffu, c0, 0);
+					left = left > c0 ? left - c0 : 0;
+					if(rc != 3) break;
+					rc = 0;
+					uint32_t m = left >= 2 ? lead_vector(io, rg, S, left, chain, lane) : 0;
+					if(m == 0) {                                   // window not applicable: one symbol through the scalar path
+						if(lane == 0) rc = clers_lead(io, rg, S, 1, false);
+						rc = __shfl_sync(0xffffffffu, rc, 0);
+						m = 1;
+					}
+					left = left > m ? left - m : 0;
+				}
+				if(lane == 0) { __threadfence_block(); st_vol_shared(&ctl[0], S.nlog); }
 				const uint32_t e0 = __shfl_sync(0xffffffffu, S.eflush, 0), nf = __shfl_sync(0xffffffffu, S.nfront, 0);
 				const uint32_t e1 = nf > WB ? nf - WB : 0u;
 				if(e1 > e0) for(uint32_t id = e0 + lane; id < e1; id += 32) {
@@ -523,13 +665,23 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 						__nanosleep(64);
 					}
 					__threadfence_block();
-					if(rc == 0 && head != F.tail) {
-						const uint32_t upto = min(head, F.tail + (uint32_t)LF_BUDGET);
-						rc = clers_follow(io, rg, F, upto, LF_STAGE, splitbits);
-					}
 				}
 				rc = __shfl_sync(0xffffffffu, rc, 0);
 				head = __shfl_sync(0xffffffffu, head, 0); done = __shfl_sync(0xffffffffu, done, 0);
+				{   // one batch of at most LF_BUDGET log words: scalar machine interleaved with warp-wide windows
+					const uint32_t t0 = __shfl_sync(0xffffffffu, F.tail, 0);
+					const uint32_t upto = min(head, t0 + (uint32_t)LF_BUDGET);
+					while(rc == 0 && __shfl_sync(0xffffffffu, F.tail, 0) < upto) {
+						if(lane == 0) rc = clers_follow(io, rg, F, upto, LF_STAGE, splitbits, vecmode);
+						rc = __shfl_sync(0xffffffffu, rc, 0);
+						if(rc != 3) break;
+						rc = 0;
+						if(follow_vector(io, rg, F, upto, lane) == 0) {    // not applicable: one word through the scalar path
+							if(lane == 0) rc = clers_follow(io, rg, F, F.tail + 1, LF_STAGE, splitbits, false);
+							rc = __shfl_sync(0xffffffffu, rc, 0);
+						}
+					}
+				}
 				// ---- drains (all lanes) ----
 				const uint32_t f0 = __shfl_sync(0xffffffffu, F.fflush, 0), f1 = __shfl_sync(0xffffffffu, F.nfaces, 0);
 				const uint32_t p0 = __shfl_sync(0xffffffffu, F.pflush, 0), p1 = __shfl_sync(0xffffffffu, F.vcount, 0);
@@ -958,7 +1110,7 @@ int launch_bit_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
 	static int mode = -1;                 // CORTO_CLERS=1w selects the single-warp machine (clers_run); default: leader / follower
-	if(mode < 0) { const char *e = getenv("CORTO_CLERS"); mode = (e && e[0] == '1') ? 1 : 2; }
+	if(mode < 0) { const char *e = getenv("CORTO_CLERS"); mode = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }   // 1: one warp, 2: leader/follower scalar, 3 (default): + window steps
 	const uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
 	if(mode == 1) {
 		uint32_t R = 4096, Q = 2048;
@@ -982,7 +1134,7 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 			if(e != cudaSuccess) return (int)e;
 			configured = smem;
 		}
-		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, RA);
+		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, RA, mode == 3);
 	}
 	LAUNCH_CHECK(); return 0;
 }

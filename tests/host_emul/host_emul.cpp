@@ -13,7 +13,95 @@
 
 using namespace crtb;
 
+// ---- host transcriptions of the warp-wide window steps of k_clers_lf (lead_vector / follow_vector, crt_kernels.cu): same
+// formulas, lanes as a loop.  They let the window logic be checked on the CPU together with the scalar machines.
+static uint32_t lead_vector_host(const ClersIO &io, ArrayRings &rg, LeadState &S, uint32_t left) {
+	const uint32_t cler = S.cler, nfront0 = S.nfront, next0 = S.cnext, nlog0 = S.nlog, eflush = S.eflush;
+	uint32_t lim = std::min(std::min(32u, left), std::min(io.nclers - cler, S.end - S.start));
+	uint32_t m = 0;
+	while(m < lim && (io.clers[cler + m] == C_VERTEX || io.clers[cler + m] == C_LEFT)) m++;
+	if(m < 2) return 0;
+	uint32_t nV = 0, nL = 0;
+	for(uint32_t j = 0; j < m; j++) { if(io.clers[cler + j] == C_VERTEX) nV++; else nL++; }
+	uint32_t chain[33];
+	uint32_t p = S.cprev; bool ok = nfront0 + nV <= io.cap;
+	for(uint32_t k = 0; k < nL; k++) {
+		chain[k] = p;
+		if(p == next0) ok = false;
+		uint32_t pp, pn;
+		if(p >= eflush) rg.ldB(p, pp, pn); else { pp = io.eb[p].prev; pn = io.eb[p].next; }
+		(void)pn;
+		p = pp;
+	}
+	chain[nL] = p;
+	if(!ok) return 0;
+	uint32_t rv = 0, rl = 0;
+	for(uint32_t j = 0; j < m; j++) {
+		if(io.clers[cler + j] == C_VERTEX) {
+			const uint32_t r = rv++, b = nfront0 + r;
+			rg.stB(b, r + 1 < nV ? b + 1 : CLERS_NOLINK, r ? b - 1 : next0);
+			rg.stFl(b, 0);
+			rg.stLog(nlog0 + j, ((uint32_t)LG_V << 28) | b);
+		} else {
+			const uint32_t q = chain[rl++];
+			if(q >= eflush) rg.stFl(q, CLERS_DEL); else io.fl[q] = CLERS_DEL;
+			rg.stLog(nlog0 + j, ((uint32_t)LG_L << 28) | q);
+		}
+	}
+	if(nV) { if(next0 >= eflush) rg.stB_prev(next0, nfront0); else io.eb[next0].prev = nfront0; }
+	S.nfront = nfront0 + nV; S.cprev = chain[nL]; if(nV) S.cnext = nfront0 + nV - 1;
+	S.lp = S.ln = 1; S.cf = CLERS_NOID; S.nlog = nlog0 + m; S.start += m;
+	const uint32_t c = cler + m, g8 = c & ~7u;
+	S.cler = c;
+	S.cw = c < io.nclers ? load_u64(io.clers + g8) >> (8u*(c & 7u)) : 0;
+	S.cw_next = g8 + 8 < io.nclers ? load_u64(io.clers + g8 + 8) : 0;
+	if(S.start >= S.end) S.have = 0;
+	return m;
+}
+
+static uint32_t follow_vector_host(const ClersIO &io, ArrayRings &rg, FollowState &F, uint32_t upto) {
+	const uint32_t tail = F.tail, lim = std::min(32u, upto - tail);
+	uint32_t ty[32], id[32], m = 0;
+	for(uint32_t j = 0; j < lim; j++) { const uint32_t w = rg.ldLog(tail + j); ty[j] = w >> 28; id[j] = w & 0x0FFFFFFFu; }
+	{
+		bool seenV = false; uint32_t firstid = 0;
+		while(m < lim && (ty[m] == LG_V || ty[m] == LG_L)) {
+			if(ty[m] == LG_V && !seenV) { seenV = true; firstid = id[m]; }
+			else if(ty[m] == LG_L && seenV && id[m] >= firstid) break;     // consumes an edge created inside this window
+			m++;
+		}
+	}
+	if(m < 2) return 0;
+	uint32_t nV = 0;
+	for(uint32_t j = 0; j < m; j++) nV += ty[j] == LG_V;
+	if(F.vcount + nV > io.nvert || F.nfaces + m > io.nface) return 0;
+	uint32_t a[32], x[32];
+	uint32_t rv = 0;
+	for(uint32_t j = 0; j < m; j++) {
+		a[j] = 0; x[j] = F.vcount + rv;
+		if(ty[j] == LG_V) rv++;
+		else { uint32_t t1, t2; if(id[j] >= F.aflush) rg.ldA(id[j], a[j], t1, t2); else a[j] = io.ea[id[j]].v0; }
+	}
+	uint32_t v0b[32], v1b[32], v0a[32], v1a[32], v2b[32];
+	uint32_t v0 = F.v0, v1 = F.v1;
+	for(uint32_t j = 0; j < m; j++) {
+		v0b[j] = v0; v1b[j] = v1;
+		if(ty[j] == LG_V) v1 = x[j]; else v0 = a[j];
+		v0a[j] = v0; v1a[j] = v1;
+	}
+	for(uint32_t j = 0; j < m; j++) v2b[j] = j == 0 ? F.v2 : (ty[j - 1] == LG_V ? v1b[j - 1] : v0b[j - 1]);
+	for(uint32_t j = 0; j < m; j++) {
+		rg.stF(F.nfaces + j, v1b[j], v0b[j], ty[j] == LG_V ? x[j] : a[j]);
+		if(ty[j] == LG_V) { rg.stP(x[j], v1b[j], v0b[j], v2b[j]); rg.stA(id[j], x[j], v1b[j], v0b[j]); F.amax = id[j] + 1; }
+	}
+	F.v0 = v0a[m - 1]; F.v1 = v1a[m - 1]; F.v2 = ty[m - 1] == LG_V ? v1b[m - 1] : v0b[m - 1];
+	F.vcount += nV; F.nfaces += m; F.tail += m;
+	return m;
+}
+
+static std::vector<uint32_t> g_log;
 extern "C" {
+int emul_log(uint32_t *out, int cap) { int n = (int)g_log.size(); for(int i = 0; i < n && i < cap; i++) out[i] = g_log[i]; return n; }
 
 // Tunstall dictionary through tun_build_seq: index[256], lengths[256], text[8192]; returns used bytes.
 int emul_tunstall_tables(const uint8_t *probs, int nsym, int *index256, int *lengths256, uint8_t *text8192) {
@@ -95,17 +183,43 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		io.fl = (uint8_t *)order.data();
 		const uint32_t W = R - 3u*budget;
 		const int splitbits = ilog2_u32(io.nvert) + 1;
+		g_log.clear();
 		LeadState L; lead_init(L, io);
 		FollowState F; follow_init(F);
 		int lrc = 0; rc = 0;
 		for(int guard = 0; guard < (1 << 30) && rc >= 0; guard++) {
-			lrc = clers_lead(io, rg, L, budget);
+			{   // one chunk, like the kernel: scalar machine + window steps
+				const bool vec = getenv("EMUL_VEC") != nullptr;
+				uint32_t left = (uint32_t)budget;
+				lrc = 0;
+				while(lrc == 0 && left > 0) {
+					const uint32_t c0 = L.cler;
+					lrc = clers_lead(io, rg, L, (int)left, vec);
+					const uint32_t used = L.cler - c0;
+					left = left > used ? left - used : 0;
+					if(lrc != 3) break;
+					lrc = 0;
+					uint32_t mm = left >= 2 ? lead_vector_host(io, rg, L, left) : 0;
+					if(mm == 0) { lrc = clers_lead(io, rg, L, 1, false); mm = 1; }
+					left = left > mm ? left - mm : 0;
+				}
+			}
+			for(uint32_t i = (uint32_t)g_log.size(); i < L.nlog; i++) g_log.push_back(lg[i & (LGN - 1)]);
 			if(lrc < 0) { rc = lrc; break; }
 			const uint32_t e1 = L.nfront > W ? L.nfront - W : 0;
 			if(e1 > L.eflush) { for(uint32_t id = L.eflush; id < e1; id++) { const uint2_t l = rb[id & (R - 1)]; eb[id] = EdgeB{l.x, l.y}; io.fl[id] = rf[id & (R - 1)]; } L.eflush = e1; }
 			while(F.tail < L.nlog && rc >= 0) {
 				const uint32_t upto = std::min(L.nlog, F.tail + (uint32_t)budget);
-				const int frc = clers_follow(io, rg, F, upto, ST, splitbits);
+				int frc = 0;
+				{
+					const bool vec = getenv("EMUL_VEC") != nullptr;
+					while(frc == 0 && F.tail < upto) {
+						frc = clers_follow(io, rg, F, upto, ST, splitbits, vec);
+						if(frc != 3) break;
+						frc = 0;
+						if(follow_vector_host(io, rg, F, upto) == 0) frc = clers_follow(io, rg, F, F.tail + 1, ST, splitbits, false);
+					}
+				}
 				for(uint32_t f = F.fflush; f < F.nfaces; f++) { const uint4_t v = sf[f & (ST - 1)]; faces[(size_t)f*3] = v.x; faces[(size_t)f*3 + 1] = v.y; faces[(size_t)f*3 + 2] = v.z; }
 				for(uint32_t v = F.pflush; v < F.vcount; v++) { const uint4_t x = sp[v & (ST - 1)]; pred[(size_t)v*4] = x.x; pred[(size_t)v*4 + 1] = x.y; pred[(size_t)v*4 + 2] = x.z; pred[(size_t)v*4 + 3] = 0; }
 				F.fflush = F.nfaces; F.pflush = F.vcount;
