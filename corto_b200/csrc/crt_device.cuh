@@ -642,7 +642,8 @@ CRT_COLD static void lead_g_set_flag(uint8_t *fl, uint32_t x, uint32_t v) { fl[x
 // edge that is queued and alive (a flag byte per edge: CLERS_DEL / CLERS_NQ).  No queue is stored.
 // Consumes at most `budget` symbols (each yields at most 2 log words, a pop 1).  Returns 1 when all groups are done, 0 to
 // be called again after the caller drained / waited for log space, 3 (only with vec) when a VERTEX/LEFT run starts and the
-// caller should run its warp-wide window step, < 0 on a topology error.  There are no exits from
+// caller should run its warp-wide window step, 4 (only with vec) when the implicit FIFO must be scanned (lead_pop_vector),
+// < 0 on a topology error.  There are no exits from
 // inside the hot paths: errors set a sticky flag and indices are clamped, the flag is reported at the chunk end.
 template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &S, int budget, bool vec = false) {
 	uint32_t cler = S.cler, start = S.start, end = S.end;
@@ -691,6 +692,7 @@ template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &
 				continue;
 			}
 			uint32_t skip = 1;
+			if(vec && scan < nfront) { rc = 4; break; }   // caller scans the flag bytes 32 at a time (k_clers_lf: lead_pop_vector)
 			while(scan < nfront) {                     // implicit FIFO: next queued, alive edge in id order
 				f = scan++;
 				skip = LD_FLAG(f);
@@ -771,7 +773,8 @@ template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &
 		}
 		if(have) break;                                    // budget used up in the middle of a strip
 	}
-	if(rc == 0 && (bad || (cler >= nclers && !(start >= end && g >= io.ngroups)))) rc = -5;   // flagged, or the stream ran dry with faces missing
+	if(rc == 0 && (bad || (cler >= nclers && !(start >= end && g >= io.ngroups)))) rc = -5;
+	if(rc == 4 && bad) rc = -5;   // flagged, or the stream ran dry with faces missing
 	S.cler = cler; S.start = start; S.end = end; S.nfront = nfront; S.scan = scan; S.ndelayed = ndel;
 	S.cw = cw; S.cw_next = cwn; S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.cprev = prev; S.cnext = next; S.g = g; S.nlog = nlog; S.bad = bad;
 	return rc;

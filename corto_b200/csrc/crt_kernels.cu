@@ -446,6 +446,7 @@ __device__ __forceinline__ void st_vol_shared(uint32_t *p, uint32_t v) { asm vol
 __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S, uint32_t left, uint32_t *chain, uint32_t lane) {
 	const uint32_t FULL = 0xffffffffu;
 	__syncwarp();                                          // lane 0's scalar ring stores are visible to every lane from here
+	if(!__shfl_sync(FULL, S.have, 0)) return 0;            // no current edge: the scalar machine has to pop one first
 	const uint32_t cler = __shfl_sync(FULL, S.cler, 0), start = __shfl_sync(FULL, S.start, 0), end = __shfl_sync(FULL, S.end, 0);
 	const uint32_t nfront0 = __shfl_sync(FULL, S.nfront, 0), next0 = __shfl_sync(FULL, S.cnext, 0), nlog0 = __shfl_sync(FULL, S.nlog, 0);
 	const uint32_t eflush = __shfl_sync(FULL, S.eflush, 0);
@@ -506,6 +507,36 @@ __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 	return m;
 }
 
+// Implicit-FIFO pop, 32 flag bytes per step: most queued edges are dead by the time the scan reaches them (a grid deletes
+// ~99 % of them), so the scalar machine would pay one dependent shared-memory load per dead edge.  On success the popped
+// edge becomes the current edge (links loaded, LG_P logged); otherwise scan == nfront and the scalar machine goes on
+// with the delayed stack / a start triangle.
+__device__ void lead_pop_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S, uint32_t lane) {
+	const uint32_t FULL = 0xffffffffu;
+	__syncwarp();
+	uint32_t scan = __shfl_sync(FULL, S.scan, 0);
+	const uint32_t nfront = __shfl_sync(FULL, S.nfront, 0), eflush = __shfl_sync(FULL, S.eflush, 0);
+	uint32_t found = CLERS_NOID;
+	while(scan < nfront) {
+		const uint32_t id = scan + lane;
+		uint32_t fl = 0xffu;
+		if(id < nfront) fl = id >= eflush ? rg.ldFl(id) : lead_g_flag(io.fl, id);
+		const uint32_t alive = __ballot_sync(FULL, fl == 0);
+		if(alive) { found = scan + (uint32_t)__ffs(alive) - 1u; scan = found + 1; break; }
+		scan += 32;
+	}
+	if(lane == 0) {
+		S.scan = scan < nfront ? scan : nfront;
+		if(found != CLERS_NOID) {
+			uint32_t p, q;
+			if(found >= eflush) rg.ldB(found, p, q); else { const uint2_t t_ = lead_g_load(io.eb, found); p = t_.x; q = t_.y; }
+			S.cprev = p; S.cnext = q; S.lp = S.ln = 0; S.have = 1; S.cf = found;
+			rg.stLog(S.nlog, ((uint32_t)LG_P << 28) | found); S.nlog++;
+		}
+	}
+	__syncwarp();
+}
+
 // Label machine over a run of VERTEX / LEFT log words: "who defined v0 / v1 last" is a bit trick on the ballot masks,
 // label loads of the LEFTs go out in parallel, faces / predictions / labels are staged by 32 lanes at once.
 __device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState &F, uint32_t upto, uint32_t lane) {
@@ -561,9 +592,9 @@ __device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState
 	return m;
 }
 
-constexpr int LF_BUDGET = 64;           // symbols per leader chunk / log words per follower batch
-constexpr uint32_t LF_STAGE = 256;      // staged faces / predictions (>= 3*LF_BUDGET)
-constexpr uint32_t LF_LOG = 1024;       // log ring words
+constexpr int LF_BUDGET = 160;          // symbols per leader chunk / log words per follower batch
+constexpr uint32_t LF_STAGE = 512;      // staged faces / predictions (>= 3*LF_BUDGET)
+constexpr uint32_t LF_LOG = 2048;       // log ring words
 constexpr uint32_t LF_SPIN = 1u << 26;  // bound on every wait loop
 
 __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
@@ -618,21 +649,27 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 				rc = __shfl_sync(0xffffffffu, rc, 0);
 				// one chunk: scalar machine, interleaved with warp-wide windows over VERTEX/LEFT runs
 				uint32_t left = LF_BUDGET;
+				bool tried = false;                                // the last window attempt bailed: one symbol goes the scalar way
 				while(rc == 0 && left > 0) {
+					if(vecmode && left >= 2 && !tried) {
+						const uint32_t m = lead_vector(io, rg, S, left, chain, lane);
+						if(m) { left = left > m ? left - m : 0; continue; }
+					}
 					uint32_t c0 = 0;
-					if(lane == 0) { c0 = S.cler; rc = clers_lead(io, rg, S, (int)left, vecmode); c0 = S.cler - c0; }
+					if(lane == 0) { c0 = S.cler; rc = clers_lead(io, rg, S, tried ? 1 : (int)left, vecmode && !tried); c0 = S.cler - c0; }
 					rc = __shfl_sync(0xffffffffu, rc, 0);
 					c0 = __shfl_sync(0xffffffffu, c0, 0);
 					left = left > c0 ? left - c0 : 0;
-					if(rc != 3) break;
-					rc = 0;
-					uint32_t m = left >= 2 ? lead_vector(io, rg, S, left, chain, lane) : 0;
-					if(m == 0) {                                   // window not applicable: one symbol through the scalar path
-						if(lane == 0) rc = clers_lead(io, rg, S, 1, false);
-						rc = __shfl_sync(0xffffffffu, rc, 0);
-						m = 1;
+					tried = false;
+					if(rc == 3) {                                  // the scalar machine saw a VERTEX/LEFT run coming
+						rc = 0;
+						const uint32_t m = left >= 2 ? lead_vector(io, rg, S, left, chain, lane) : 0;
+						if(m) left = left > m ? left - m : 0; else tried = true;
+					} else if(rc == 4) {                           // it needs the next queued edge
+						rc = 0;
+						lead_pop_vector(io, rg, S, lane);
+						if(!__shfl_sync(0xffffffffu, S.have, 0)) tried = true;   // queue exhausted: scalar path (delayed stack / start triangle)
 					}
-					left = left > m ? left - m : 0;
 				}
 				if(lane == 0) { __threadfence_block(); st_vol_shared(&ctl[0], S.nlog); }
 				const uint32_t e0 = __shfl_sync(0xffffffffu, S.eflush, 0), nf = __shfl_sync(0xffffffffu, S.nfront, 0);
@@ -671,15 +708,13 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 				{   // one batch of at most LF_BUDGET log words: scalar machine interleaved with warp-wide windows
 					const uint32_t t0 = __shfl_sync(0xffffffffu, F.tail, 0);
 					const uint32_t upto = min(head, t0 + (uint32_t)LF_BUDGET);
+					bool tried = false;
 					while(rc == 0 && __shfl_sync(0xffffffffu, F.tail, 0) < upto) {
-						if(lane == 0) rc = clers_follow(io, rg, F, upto, LF_STAGE, splitbits, vecmode);
+						if(vecmode && !tried && follow_vector(io, rg, F, upto, lane)) continue;
+						if(lane == 0) rc = clers_follow(io, rg, F, tried ? F.tail + 1 : upto, LF_STAGE, splitbits, vecmode && !tried);
 						rc = __shfl_sync(0xffffffffu, rc, 0);
-						if(rc != 3) break;
-						rc = 0;
-						if(follow_vector(io, rg, F, upto, lane) == 0) {    // not applicable: one word through the scalar path
-							if(lane == 0) rc = clers_follow(io, rg, F, F.tail + 1, LF_STAGE, splitbits, false);
-							rc = __shfl_sync(0xffffffffu, rc, 0);
-						}
+						tried = false;
+						if(rc == 3) { rc = 0; if(follow_vector(io, rg, F, upto, lane) == 0) tried = true; }
 					}
 				}
 				// ---- drains (all lanes) ----

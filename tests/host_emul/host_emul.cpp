@@ -59,6 +59,21 @@ static uint32_t lead_vector_host(const ClersIO &io, ArrayRings &rg, LeadState &S
 	return m;
 }
 
+static void lead_pop_host(const ClersIO &io, ArrayRings &rg, LeadState &S) {
+	uint32_t found = CLERS_NOID;
+	while(S.scan < S.nfront) {
+		const uint32_t id = S.scan++;
+		const uint32_t fl = id >= S.eflush ? rg.ldFl(id) : io.fl[id];
+		if(fl == 0) { found = id; break; }
+	}
+	if(found != CLERS_NOID) {
+		uint32_t p, q;
+		if(found >= S.eflush) rg.ldB(found, p, q); else { p = io.eb[found].prev; q = io.eb[found].next; }
+		S.cprev = p; S.cnext = q; S.lp = S.ln = 0; S.have = 1; S.cf = found;
+		rg.stLog(S.nlog, ((uint32_t)LG_P << 28) | found); S.nlog++;
+	}
+}
+
 static uint32_t follow_vector_host(const ClersIO &io, ArrayRings &rg, FollowState &F, uint32_t upto) {
 	const uint32_t tail = F.tail, lim = std::min(32u, upto - tail);
 	uint32_t ty[32], id[32], m = 0;
@@ -192,16 +207,16 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 				const bool vec = getenv("EMUL_VEC") != nullptr;
 				uint32_t left = (uint32_t)budget;
 				lrc = 0;
+				bool tried = false;
 				while(lrc == 0 && left > 0) {
+					if(vec && left >= 2 && !tried && L.have) { const uint32_t mm = lead_vector_host(io, rg, L, left); if(mm) { left = left > mm ? left - mm : 0; continue; } }
 					const uint32_t c0 = L.cler;
-					lrc = clers_lead(io, rg, L, (int)left, vec);
+					lrc = clers_lead(io, rg, L, tried ? 1 : (int)left, vec && !tried);
 					const uint32_t used = L.cler - c0;
 					left = left > used ? left - used : 0;
-					if(lrc != 3) break;
-					lrc = 0;
-					uint32_t mm = left >= 2 ? lead_vector_host(io, rg, L, left) : 0;
-					if(mm == 0) { lrc = clers_lead(io, rg, L, 1, false); mm = 1; }
-					left = left > mm ? left - mm : 0;
+					tried = false;
+					if(lrc == 3) { lrc = 0; const uint32_t mm = left >= 2 ? lead_vector_host(io, rg, L, left) : 0; if(mm) left = left > mm ? left - mm : 0; else tried = true; }
+					else if(lrc == 4) { lrc = 0; lead_pop_host(io, rg, L); if(!L.have) tried = true; }
 				}
 			}
 			for(uint32_t i = (uint32_t)g_log.size(); i < L.nlog; i++) g_log.push_back(lg[i & (LGN - 1)]);
