@@ -75,6 +75,8 @@ struct crt_batch {
 	uint8_t *d_symbols = nullptr, *d_tunrec = nullptr; uint32_t *d_tun_used = nullptr;
 	ClersScratch clers{};
 	bool uploaded = false;
+	uint64_t signature = 0;            // of the directory + bindings the device tables were built from
+	size_t dir_bytes = 0;              // prefix of the table image that holds the directory
 	int launches = 0;
 	bool profiling = false;
 	std::vector<Stage> stages;
@@ -316,6 +318,8 @@ template <class T> static size_t put(std::vector<uint8_t> &img, const std::vecto
 	return o;
 }
 
+static uint64_t directory_signature(const crt_batch *b);
+
 static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	CU(cudaGetDevice(&b->device));
 	CU(cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, b->device));
@@ -403,6 +407,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->o_mesh = put(img, b->h_mesh);
 	b->o_tun = put(img, b->h_tun);
 	b->o_groups = put(img, b->h_groups);
+	b->dir_bytes = img.size();              // MeshDesc | TunDesc | groups: the directory proper
 	b->o_t_tun = put(img, b->t_tun);
 	b->o_t_bits = put(img, b->t_bits);
 	b->o_t_cloud = put(img, b->t_cloud);
@@ -421,6 +426,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	// the table image is pageable host memory owned by the batch; wait so it may be rebuilt safely
 	CU(cudaStreamSynchronize(stream));
 	b->uploaded = true;
+	b->signature = directory_signature(b);
 	return CRT_OK;
 }
 
@@ -429,12 +435,37 @@ extern "C" int crt_batch_upload(crt_batch *b, void *stream) {
 	return batch_prepare(b, (cudaStream_t)stream, true);
 }
 
+// Signature of a walked directory: every offset / size the device tables are derived from.
+static uint64_t directory_signature(const crt_batch *b) {
+	uint64_t h = 0xcbf29ce484222325ull;
+	auto mix = [&](uint64_t v) { h ^= v; h *= 0x100000001b3ull; };
+	auto blk = [&](const Block &k) { mix(k.probs_off); mix(k.nsym); mix(k.size); mix(k.csize); mix(k.data_off); mix(k.raw); };
+	for(const ParsedMesh &m: b->meshes) {
+		mix(m.nvert); mix(m.nface); mix(m.max_front); mix(m.split_off); mix(m.split_nwords);
+		for(uint32_t e: m.group_ends) mix(e);
+		blk(m.clers);
+		for(const AttrStreams &s: m.streams) {
+			mix(s.bits_off); mix(s.bits_nwords); mix((uint64_t)s.prediction);
+			for(int k = 0; k < 4; k++) mix((uint64_t)s.qc[k]);
+			for(const Block &k: s.blocks) blk(k);
+		}
+	}
+	for(auto &kv: b->binds) { for(char c: kv.first) mix((uint64_t)c); mix((uint64_t)kv.second.ptr); mix((uint64_t)kv.second.format); mix((uint64_t)kv.second.components); }
+	return h;
+}
+
 extern "C" int crt_batch_rewalk(crt_batch *b, void *stream) {
 	if(!b->uploaded) return fail(CRT_E_ARG, "crt_batch_rewalk before crt_batch_upload");
 	for(size_t i = 0; i < b->meshes.size(); i++) {
 		std::string err;
 		int rc = walk_directory(b->meshes[i], err);
 		if(rc) return fail(rc, "blob " + std::to_string(i) + ": " + err);
+	}
+	// The directory (MeshDesc / TunDesc / group table) goes to the device again.  The launch geometry derived from it (tile
+	// lists, work orders) is a pure function of the directory: it is rebuilt only when the walk found something different.
+	if(directory_signature(b) == b->signature && b->dir_bytes) {
+		CU(cudaMemcpyAsync(b->d_tables, b->h_tables.data(), b->dir_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+		return CRT_OK;
 	}
 	return batch_prepare(b, (cudaStream_t)stream, false);
 }

@@ -801,22 +801,25 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 #pragma unroll
 			for(int k = 0; k < NC; k++) x_next[k] = in2 < nvert ? (uint32_t)v[(size_t)in2*NC + k] : 0u;
 		}
-		// pure chain: every in-block operand is "a = previous lane"
-		const bool chain_ok = !act || (!b_in && !c_in && (!a_in || a == i - 1));
-		if(__all_sync(0xffffffffu, chain_ok)) {
+		// fast path: b and c outside the block, a anywhere EARLIER in the block (or outside): x_i = r_i + x_parent(i) is a forest
+		// whose parents have lower lane numbers -> pointer doubling, 5 shuffle rounds (a chain a = i-1, 99.7 % of a grid, and
+		// the strip starts in between are both covered)
+		const bool tree_ok = !act || (!b_in && !c_in && (!a_in || a < i));
+		if(__all_sync(0xffffffffu, tree_ok)) {
+			uint32_t parent = a_in ? (a - base) : 0xffffffffu;     // lane of the in-block parent, or none
+			uint32_t r[NC];
 #pragma unroll
-			for(int k = 0; k < NC; k++) {
-				// r = everything except the in-block a term; lanes whose a is outside (or inactive) start a new segment
-				uint32_t r = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k];
-				uint32_t val = r; bool flag = !a_in;       // segmented inclusive scan: value + "segment head" flag
+			for(int k = 0; k < NC; k++) r[k] = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k];
 #pragma unroll
-				for(int d = 1; d < 32; d <<= 1) {
-					const uint32_t ov = __shfl_up_sync(0xffffffffu, val, d);
-					const bool of = __shfl_up_sync(0xffffffffu, (int)flag, d) != 0;
-					if(lane >= d && !flag) { val += ov; flag = of; }
-				}
-				x[k] = val;
+			for(int d = 0; d < 5; d++) {
+				const uint32_t src = parent == 0xffffffffu ? (uint32_t)lane : parent;
+				const uint32_t pp = __shfl_sync(0xffffffffu, parent, src);
+#pragma unroll
+				for(int k = 0; k < NC; k++) { const uint32_t pr = __shfl_sync(0xffffffffu, r[k], src); if(parent != 0xffffffffu) r[k] += pr; }
+				if(parent != 0xffffffffu) parent = pp;
 			}
+#pragma unroll
+			for(int k = 0; k < NC; k++) x[k] = r[k];
 		} else {
 			for(int j = 0; j < 32; j++) {
 				const uint32_t aj = __shfl_sync(0xffffffffu, a, j), bj = __shfl_sync(0xffffffffu, b, j), cj = __shfl_sync(0xffffffffu, c, j);
