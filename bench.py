@@ -38,7 +38,7 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    p.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "tarta"])
     p.add_argument("--batch", type=int, default=None, help="meshes per GPU (default: 256 for c2, 512 c3, 512 c4, 1 c1/c5)")
     p.add_argument("--distinct", type=int, default=None, help="distinct seeds to encode (default: all)")
     p.add_argument("--no-e2e", action="store_true")
@@ -46,7 +46,7 @@ def parse():
     return p.parse_args()
 
 
-DEFAULT_BATCH = dict(c1=1, c2=256, c3=512, c4=512, c5=1)
+DEFAULT_BATCH = dict(c1=1, c2=256, c3=512, c4=512, c5=1, tarta=64)
 
 
 def peaks():

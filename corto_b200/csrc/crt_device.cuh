@@ -626,11 +626,12 @@ struct LeadState {
 	uint32_t have, lp, ln, cf, cprev, cnext;
 	uint32_t eflush;
 	uint32_t nlog, bad;
+	uint32_t cwv;                      // 0: cw / cw_next are stale (a window step moved cler), re-prime on entry
 };
 CRT_HD void lead_init(LeadState &S, const ClersIO &io) {
 	S.cler = 0; S.cw = io.nclers ? load_u64(io.clers) : 0; S.cw_next = io.nclers > 8 ? load_u64(io.clers + 8) : 0;
 	S.g = 0; S.start = S.end = 0; S.nfront = S.scan = S.ndelayed = 0;
-	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.cprev = S.cnext = 0; S.eflush = 0; S.nlog = 0; S.bad = 0;
+	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.cprev = S.cnext = 0; S.eflush = 0; S.nlog = 0; S.bad = 0; S.cwv = 1;
 }
 
 CRT_COLD static uint2_t lead_g_load(const EdgeB *eb, uint32_t x) { const EdgeB l = eb[x]; return uint2_t{l.prev, l.next}; }
@@ -648,6 +649,12 @@ CRT_COLD static void lead_g_set_flag(uint8_t *fl, uint32_t x, uint32_t v) { fl[x
 template <class RG> CRT_HD int clers_lead(const ClersIO &io, RG &rg, LeadState &S, int budget, bool vec = false) {
 	uint32_t cler = S.cler, start = S.start, end = S.end;
 	uint32_t nfront = S.nfront, scan = S.scan, ndel = S.ndelayed, nlog = S.nlog, bad = S.bad;
+	if(!S.cwv) {                                   // re-prime the 8-byte symbol window after a warp-wide step
+		const uint32_t g8 = cler & ~7u;
+		S.cw = cler < io.nclers ? load_u64(io.clers + g8) >> (8u*(cler & 7u)) : 0;
+		S.cw_next = g8 + 8 < io.nclers ? load_u64(io.clers + g8 + 8) : 0;
+		S.cwv = 1;
+	}
 	uint64_t cw = S.cw, cwn = S.cw_next;
 	uint32_t have = S.have, lp = S.lp, ln = S.ln, f = S.cf, prev = S.cprev, next = S.cnext, g = S.g;
 	const uint32_t eflush = S.eflush, nclers = io.nclers, cap = io.cap;

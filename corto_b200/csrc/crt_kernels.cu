@@ -497,10 +497,7 @@ __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 		if(nV) S.cnext = nfront0 + nV - 1;
 		S.lp = S.ln = 1; S.cf = CLERS_NOID;
 		S.nlog = nlog0 + m; S.start = start + m;
-		const uint32_t c = cler + m, g8 = c & ~7u;          // re-prime the 8-byte symbol window
-		S.cler = c;
-		S.cw = c < io.nclers ? load_u64(io.clers + g8) >> (8u*(c & 7u)) : 0;
-		S.cw_next = g8 + 8 < io.nclers ? load_u64(io.clers + g8 + 8) : 0;
+		S.cler = cler + m; S.cwv = 0;                       // the scalar machine re-primes its symbol window when it next runs
 		if(S.start >= S.end) S.have = 0;
 	}
 	__syncwarp();
@@ -796,6 +793,12 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 			fc[k] = (act && par && !c_in && c < nvert) ? (uint32_t)v[(size_t)c*NC + k] : 0u;
 		}
 		{
+			// the streams read one round ahead (prediction, residuals) come from DRAM: pull them into L2 several rounds earlier
+			const uint32_t far = i + 32u*8u;
+			if(far < nvert) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(pred + far));
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(v + (size_t)far*NC));
+			}
 			const uint32_t in2 = i + 32;
 			p_next = in2 < nvert ? pred[in2] : make_uint4(0, 0, 0, 0);
 #pragma unroll

@@ -48,7 +48,11 @@ def _c5(seed):
                           with_colors=False)[0]
 
 
-_BUILDERS = dict(c1=_c1, c2=_c2, c3=_c3, c4=_c4, c5=_c5)
+def _tarta(seed):
+    return refshim.aligned_blob(open(refshim.TARTA, 'rb').read())
+
+
+_BUILDERS = dict(c1=_c1, c2=_c2, c3=_c3, c4=_c4, c5=_c5, tarta=_tarta)
 
 DESCRIPTION = dict(
     c1="185^2 grid 34K verts pos14 (bunny stand-in)",
@@ -56,6 +60,7 @@ DESCRIPTION = dict(
     c3="409^2 cloud 167K verts pos14/color6/normal10-DIFF (Nile stand-in)",
     c4="mixed grids 8K-256K verts, all attributes + groups",
     c5="3163^2 grid 10M verts pos14/normal10-BORDER",
+    tarta="html/models/tarta.crt (real scan, 1.71M verts / 3.29M faces, pos+uv), replicated",
 )
 
 
@@ -64,6 +69,8 @@ def build(workload, batch, seed0=1, distinct=None, threads=None):
     are repeats in round-robin order (encoding is the slow part of set-up, not something the benchmark measures)."""
     fn = _BUILDERS[workload]
     distinct = batch if distinct is None else max(1, min(distinct, batch))
+    if workload == 'tarta':
+        distinct = 1
     threads = threads or min(32, os.cpu_count() or 1)
     seeds = [seed0 + i for i in range(distinct)]
     with ThreadPoolExecutor(max_workers=threads) as ex:

@@ -51,10 +51,7 @@ static uint32_t lead_vector_host(const ClersIO &io, ArrayRings &rg, LeadState &S
 	if(nV) { if(next0 >= eflush) rg.stB_prev(next0, nfront0); else io.eb[next0].prev = nfront0; }
 	S.nfront = nfront0 + nV; S.cprev = chain[nL]; if(nV) S.cnext = nfront0 + nV - 1;
 	S.lp = S.ln = 1; S.cf = CLERS_NOID; S.nlog = nlog0 + m; S.start += m;
-	const uint32_t c = cler + m, g8 = c & ~7u;
-	S.cler = c;
-	S.cw = c < io.nclers ? load_u64(io.clers + g8) >> (8u*(c & 7u)) : 0;
-	S.cw_next = g8 + 8 < io.nclers ? load_u64(io.clers + g8 + 8) : 0;
+	S.cler = cler + m; S.cwv = 0;
 	if(S.start >= S.end) S.have = 0;
 	return m;
 }
