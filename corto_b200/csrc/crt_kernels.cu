@@ -460,10 +460,23 @@ __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 	const uint32_t Vm = __ballot_sync(FULL, isV) & pm, Lm = __ballot_sync(FULL, isL) & pm;
 	const uint32_t nV = __popc(Vm), nL = __popc(Lm);
 	uint32_t ok = 1;
+	// Fast path for the prev chain: the edges a strip consumes on its left are usually the queued edges of ONE earlier strip,
+	// created back to back and linked in creation order (prev of id k is k+1).  Every lane checks one link; if all of them
+	// hold the chain is p0, p0+1, ... and nothing is walked.  Any mismatch falls back to the serial walk.
+	const uint32_t p0 = __shfl_sync(FULL, S.cprev, 0);
+	bool consecutive = false;
+	if(nL) {
+		const uint32_t idk = p0 + lane;
+		uint32_t pk = 0xffffffffu, pn;
+		if(lane < nL && idk >= eflush && idk < nfront0 && idk != next0) rg.ldB(idk, pk, pn);
+		consecutive = __all_sync(FULL, lane >= nL || pk == idk + 1);
+		if(consecutive && lane <= nL) chain[lane] = p0 + lane;
+		if(consecutive && lane == 0) chain[nL] = p0 + nL;
+	}
 	if(lane == 0) {
 		uint32_t p = S.cprev;
 		if(nfront0 + nV > io.cap) ok = 0;
-		for(uint32_t k = 0; k < nL; k++) {                 // the serial part: walk the prev chain
+		for(uint32_t k = 0; k < nL && !consecutive; k++) {   // the serial part: walk the prev chain
 			chain[k] = p;
 			if(p == next0) ok = 0;                         // the walk wraps around to the right-hand neighbour (small loop): its links
 			                                               // change inside this window, so take the scalar path
@@ -472,7 +485,7 @@ __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 			(void)pn;
 			p = pp;
 		}
-		chain[nL] = p;
+		if(!consecutive) chain[nL] = p;
 	}
 	__syncwarp();
 	ok = __shfl_sync(FULL, ok, 0);
@@ -824,24 +837,34 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 #pragma unroll
 			for(int k = 0; k < NC; k++) x[k] = r[k];
 		} else {
-			for(int j = 0; j < 32; j++) {
-				const uint32_t aj = __shfl_sync(0xffffffffu, a, j), bj = __shfl_sync(0xffffffffu, b, j), cj = __shfl_sync(0xffffffffu, c, j);
-				const int fl = __shfl_sync(0xffffffffu, (int)act | ((int)a_in << 1) | ((int)b_in << 2) | ((int)c_in << 3), j);
-				if(!(fl & 1)) continue;
+			// general case (operands b / c inside the block, common on irregular meshes): lanes are finalised in order; lane j's
+			// final value is pushed to every later lane that names it.  A lane is final once all lower lanes were pushed, and an
+			// operand naming a HIGHER lane (hostile stream) reads that lane's residual, exactly like the in-place reference loop.
+			const uint32_t la = a_in ? a - base : 64u, lb = b_in ? b - base : 64u, lc = c_in ? c - base : 64u;
+			uint32_t acc[NC], res[NC];
+#pragma unroll
+			for(int k = 0; k < NC; k++) { res[k] = x[k]; acc[k] = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k]; }
+			// operands that point at this lane or a higher one never become final before this lane: they contribute residuals
+#pragma unroll
+			for(int k = 0; k < NC; k++) {
+				const uint32_t ra = __shfl_sync(0xffffffffu, res[k], la & 31u), rb = __shfl_sync(0xffffffffu, res[k], lb & 31u), rc = __shfl_sync(0xffffffffu, res[k], lc & 31u);
+				if(la < 32u && la >= (uint32_t)lane) acc[k] += ra;
+				if(lb < 32u && lb >= (uint32_t)lane) acc[k] += rb;
+				if(lc < 32u && lc >= (uint32_t)lane) acc[k] -= rc;
+			}
+			const uint32_t named = __reduce_or_sync(0xffffffffu, (la < (uint32_t)lane ? 1u << la : 0u) | (lb < (uint32_t)lane ? 1u << lb : 0u) | (lc < (uint32_t)lane ? 1u << lc : 0u));
+			for(uint32_t todo = named; todo; todo &= todo - 1) {
+				const int j = __ffs(todo) - 1;             // every lane below j that anyone names has been pushed already, so acc of lane j is final
 #pragma unroll
 				for(int k = 0; k < NC; k++) {
-					// x of an in-block lane is final if that lane was processed already, else still its residual: exactly what
-					// the in-place sequential loop would read
-					const uint32_t xa = __shfl_sync(0xffffffffu, x[k], (aj - base) & 31u);
-					const uint32_t xb = __shfl_sync(0xffffffffu, x[k], (bj - base) & 31u);
-					const uint32_t xc = __shfl_sync(0xffffffffu, x[k], (cj - base) & 31u);
-					if(lane == j) {
-						uint32_t r = x[k] + ((fl & 2) ? xa : fa[k]);
-						if(par) r = r + ((fl & 4) ? xb : fb[k]) - ((fl & 8) ? xc : fc[k]);
-						x[k] = r;
-					}
+					const uint32_t xj = __shfl_sync(0xffffffffu, acc[k], j);
+					if(la == (uint32_t)j) acc[k] += xj;
+					if(lb == (uint32_t)j) acc[k] += xj;
+					if(lc == (uint32_t)j) acc[k] -= xj;
 				}
 			}
+#pragma unroll
+			for(int k = 0; k < NC; k++) x[k] = acc[k];
 		}
 		if(act) {
 #pragma unroll
@@ -1168,6 +1191,7 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 		// few meshes: big rings (2 CTAs per SM);  many meshes: small rings so that more serial chains share an SM
 		uint32_t RB = 4096, RA = 2048;
 		if(nwork > (uint32_t)sms*2u) { RB = 1024; RA = 1024; }
+		else if(nwork <= (uint32_t)sms) { RB = 16384; RA = 2048; }   // one mesh per SM at most: the whole shared memory for its rings
 		const size_t smem = (size_t)RB*9 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
 		static size_t configured = 0;
 		if(configured < smem) {
