@@ -152,10 +152,18 @@ def test_device_cores_on_cpu(emul, name):
         assert np.array_equal(i1, i2) and np.array_equal(l1, l2) and np.array_equal(t1[:u1], t2[:u1])
     o = pyoracle.decode(blob, debug=True)
     if o["nface"]:
-        for ring in ((0, 0), (-64, 64), (-128, 64), (-4096, 2048)):
-            faces = np.zeros((o["nface"], 3), np.uint32); pred = np.zeros((o["nvert"], 3), np.uint32)
-            rc = emul.emul_clers(_p(blob), len(blob), _p(o["clers"]), len(o["clers"]), _p(faces), _p(pred), ring[0], ring[1])
-            assert rc == 0 and np.array_equal(faces, o["index"]) and np.array_equal(pred[1:], o["prediction"][1:]), (name, ring)
+        # (R, Q): 0,0 = clers_decode_seq; R<0 = single-warp machine clers_run; R>0,Q<0 = leader/follower (clers_lead + clers_follow),
+        # with EMUL_VEC also the host transcriptions of the kernel's warp-wide window steps (lead_vector / follow_vector / lead_pop_vector)
+        for vec in (False, True):
+            if vec:
+                os.environ["EMUL_VEC"] = "1"
+            else:
+                os.environ.pop("EMUL_VEC", None)
+            for ring in ((0, 0), (-64, 64), (-128, 64), (-4096, 2048), (64, -64), (256, -256), (4096, -2048)):
+                faces = np.zeros((o["nface"], 3), np.uint32); pred = np.zeros((o["nvert"], 3), np.uint32)
+                rc = emul.emul_clers(_p(blob), len(blob), _p(o["clers"]), len(o["clers"]), _p(faces), _p(pred), ring[0], ring[1])
+                assert rc == 0 and np.array_equal(faces, o["index"]) and np.array_equal(pred[1:], o["prediction"][1:]), (name, ring, vec)
+        os.environ.pop("EMUL_VEC", None)
 
 
 # ---- multi-rank sharding over gloo, world_size 2 ---------------------------------------------------------------------
