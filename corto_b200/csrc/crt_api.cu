@@ -52,7 +52,7 @@ struct crt_batch {
 	std::vector<MeshDesc> h_mesh;
 	std::vector<TunDesc> h_tun;
 	std::vector<uint32_t> h_groups;
-	std::vector<Tile> t_tun, t_bits, t_cloud, t_dequant, t_faces, t_verts, t_vscan;
+	std::vector<Tile> t_tun, t_bits, t_cloud, t_dequant, t_faces, t_verts, t_vscan, t_cfused;
 	std::vector<uint2> w_delta;
 	std::vector<uint32_t> clers_order;
 	bool any_border = false;
@@ -67,9 +67,9 @@ struct crt_batch {
 	std::vector<uint8_t> h_pinned_stage;
 	// offsets inside d_tables
 	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_cloud = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
-	       o_t_vscan = 0, o_w_delta = 0, o_order = 0;
+	       o_t_vscan = 0, o_w_delta = 0, o_order = 0, o_t_cfused = 0;
 	// offsets inside d_zero
-	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_states = 0, z_csr = 0;
+	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_states = 0, z_csr = 0, z_tunbits = 0;
 	size_t n_states = 0;
 	// scratch pieces
 	uint8_t *d_symbols = nullptr, *d_tunrec = nullptr; uint32_t *d_tun_used = nullptr;
@@ -157,7 +157,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 	const int n = (int)b->meshes.size();
 	b->h_mesh.assign(n, MeshDesc{});
 	b->h_tun.clear(); b->h_groups.clear();
-	b->t_tun.clear(); b->t_bits.clear(); b->t_cloud.clear(); b->t_dequant.clear(); b->t_faces.clear(); b->t_verts.clear(); b->t_vscan.clear();
+	b->t_tun.clear(); b->t_bits.clear(); b->t_cloud.clear(); b->t_dequant.clear(); b->t_faces.clear(); b->t_verts.clear(); b->t_vscan.clear(); b->t_cfused.clear();
 	b->w_delta.clear(); b->clers_order.clear();
 	b->any_border = false;
 	symbols_bytes = 0; work_bytes = 0; zero_csr_bytes = 0; adj_bytes = 0;
@@ -259,6 +259,16 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			if(!bound) continue;
 			if(pa.codec == CODEC_NORMAL) attr_work[a] = take((uint64_t)pm.nvert*8 + 16);
 			if(pa.codec == CODEC_COLOR) attr_work[a] = take((uint64_t)pm.nvert*pa.N + 16);
+			const bool normal_diff = pa.codec == CODEC_NORMAL && st.prediction == N_DIFF;
+			if(pm.nface == 0) {
+				// point cloud: one fused kernel (bit unpack -> running delta -> dequantise) per attribute; normals other than DIFF are
+				// parsed only (the reference's cloud path runs no postDelta, decoder.cpp:133-147)
+				if(pa.codec != CODEC_NORMAL || normal_diff) {
+					uint32_t nt = (pm.nvert + 1023)/1024;
+					for(uint32_t t = 0; t < nt; t++) b->t_cfused.push_back(Tile{(uint32_t)i, (uint32_t)a, t, t == 0 ? 1u : 0u});
+				}
+				continue;
+			}
 			// bit-unpack tiles: chain = all component streams of the attribute
 			const bool correlated = pa.codec == CODEC_NORMAL || (pa.codec == CODEC_GENERIC && (pa.strategy & S_CORRELATED));
 			bool first = true;
@@ -267,7 +277,6 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 				for(uint32_t t = 0; t < nt; t++) { b->t_bits.push_back(Tile{(uint32_t)i, (uint32_t)(a | ((correlated ? 0 : k) << 8)), t, first ? 1u : 0u}); first = false; }
 			}
 			// delta inverse
-			const bool normal_diff = pa.codec == CODEC_NORMAL && st.prediction == N_DIFF;
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
 				if(pm.nface) b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a));
 				else {
@@ -368,12 +377,13 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->clers.delayed = (uint32_t *)cs;
 
 	// ---- zeroed control region: tickets | status | vertex_count | look-back states | csr counters ----
-	b->n_states = b->t_tun.size() + b->t_bits.size() + b->t_cloud.size() + 2*b->t_vscan.size();
+	b->n_states = b->t_tun.size() + b->t_bits.size() + b->t_cloud.size() + 2*b->t_vscan.size() + 8*b->t_cfused.size();
 	b->z_ticket = 0;
 	b->z_status = 256;
 	b->z_vcount = align_up(b->z_status + (uint64_t)n*4, 256);
 	b->z_states = align_up(b->z_vcount + (uint64_t)n*4, 256);
-	b->z_csr = align_up(b->z_states + b->n_states*8, 256);
+	b->z_tunbits = align_up(b->z_states + b->n_states*8, 256);
+	b->z_csr = align_up(b->z_tunbits + ntun*8, 256);
 	uint64_t zero_total = b->z_csr + csr_bytes + 256;
 	if(!b->d_zero || b->zero_bytes < zero_total) {
 		if(b->d_zero) { cudaFree(b->d_zero); b->d_zero = nullptr; }
@@ -417,6 +427,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->o_t_vscan = put(img, b->t_vscan);
 	b->o_w_delta = put(img, b->w_delta);
 	b->o_order = put(img, b->clers_order);
+	b->o_t_cfused = put(img, b->t_cfused);
 	if(!b->d_tables || b->tables_bytes < img.size()) {
 		if(b->d_tables) { cudaFree(b->d_tables); b->d_tables = nullptr; }
 		CU(cudaMalloc(&b->d_tables, img.size() + 256));
@@ -492,6 +503,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	B.group_ends = (const uint32_t *)(b->d_tables + b->o_groups);
 	B.status = (int32_t *)(b->d_zero + b->z_status);
 	B.vertex_count = (uint32_t *)(b->d_zero + b->z_vcount);
+	B.tun_bits = (unsigned long long *)(b->d_zero + b->z_tunbits);
 	uint32_t *tickets = (uint32_t *)(b->d_zero + b->z_ticket);
 	uint64_t *states = (uint64_t *)(b->d_zero + b->z_states);
 	const Tile *t_tun = (const Tile *)(b->d_tables + b->o_t_tun), *t_bits = (const Tile *)(b->d_tables + b->o_t_bits),
@@ -513,6 +525,9 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_bit_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st, tickets + 1, b->sms, s), !b->t_bits.empty());
 	st += b->t_bits.size();
 	if((rc = mark(b, "bit_unpack", k, s))) return rc;
+	RUN(launch_cloud_fused(B, (const Tile *)(b->d_tables + b->o_t_cfused), (uint32_t)b->t_cfused.size(), st, tickets + 6, b->sms, s), !b->t_cfused.empty());
+	st += 8*b->t_cfused.size();
+	if((rc = mark(b, "cloud_fused", k, s))) return rc;
 	RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
 	if((rc = mark(b, "clers", k, s))) return rc;
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());

@@ -86,6 +86,27 @@ __device__ uint64_t lookback(uint64_t *states, uint32_t t, bool first, uint64_t 
 	return excl;
 }
 
+// Same, for chains interleaved in one state array: the state of (tile t, slot k) lives at states[t*stride + k].
+__device__ uint64_t lookback_strided(uint64_t *states, uint32_t t, uint32_t stride, uint32_t slot, bool first, uint64_t aggregate) {
+	aggregate &= LB_MASK;
+	uint64_t *me = states + (size_t)t*stride + slot;
+	if(first) { lb_store(me, LB_PFX | aggregate); return 0; }
+	lb_store(me, LB_AGG | aggregate);
+	uint64_t excl = 0;
+	const uint64_t *p = me - stride;
+	for(;;) {
+		const uint64_t s = lb_load(p);
+		const uint64_t flag = s >> 62;
+		if(flag == 0) continue;
+		excl += s & LB_MASK;
+		if(flag == 2) break;
+		p -= stride;
+	}
+	excl &= LB_MASK;
+	lb_store(me, LB_PFX | ((excl + aggregate) & LB_MASK));
+	return excl;
+}
+
 // exclusive scan of one u32 per thread across a 256-thread CTA; returns the exclusive prefix, total in *total.
 __device__ __forceinline__ uint32_t cta_scan_excl_256(uint32_t v, uint32_t *s_warp /*[9]*/, uint32_t *total) {
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -143,12 +164,15 @@ __global__ void __launch_bounds__(32) k_tun_tables(DevBatch B) {
 }
 
 // =========================================================================================================
+constexpr uint32_t TUN_STAGE = 16384;   // output bytes of one tile assembled in shared memory (mean expansion is 2.6-4.5x of 2048)
+
 // K2  Tunstall decode:  out_off[i] = sum_{j<i} len[data[j]];  byte i copies its word;  the last byte of a block
 //     copies exactly the remainder (tunstall.cpp:446-451).  Raw (NONE) and single-symbol blocks are copies/fills.
 // =========================================================================================================
 __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
 	__shared__ __align__(16) uint32_t s_entry[256];
 	__shared__ __align__(16) uint8_t s_text[TUN_TABLE_BYTES];
+	__shared__ __align__(16) uint8_t s_stage[TUN_STAGE];
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ uint32_t s_warp[9];
 	__shared__ uint32_t s_tile;
@@ -166,8 +190,12 @@ __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tile
 			// tile covers TUN_TILE*4 output bytes
 			const uint32_t lo = tl.tile*(TUN_TILE*4u);
 			uint32_t hi = lo + TUN_TILE*4u; if(hi > td.size) hi = td.size;
-			if(td.raw) { const uint8_t *in = B.blobs + td.data_off; for(uint32_t i = lo + tid; i < hi; i += 256) out[i] = in[i]; }
-			else { const uint8_t sym = td.nsym ? B.blobs[td.probs_off] : 0; for(uint32_t i = lo + tid; i < hi; i += 256) out[i] = sym; }
+			uint32_t ssum = 0;
+			if(td.raw) { const uint8_t *in = B.blobs + td.data_off; for(uint32_t i = lo + tid; i < hi; i += 256) { const uint8_t v = in[i]; out[i] = v; ssum += v; } }
+			else { const uint8_t sym = td.nsym ? B.blobs[td.probs_off] : 0; for(uint32_t i = lo + tid; i < hi; i += 256) { out[i] = sym; ssum += sym; } }
+#pragma unroll
+			for(int d = 16; d; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+			if((tid & 31) == 0 && ssum) atomicAdd(B.tun_bits + tl.a, (unsigned long long)ssum);
 			continue;
 		}
 		// stage the dictionary (entries + used text) with one TMA bulk copy per part
@@ -193,18 +221,40 @@ __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tile
 		uint32_t off = cta_scan_excl_256(mylen, s_warp, &total);
 		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
 		__syncthreads();
-		uint64_t o = s_base + off;
+		const uint64_t obase = s_base;
+		uint32_t ssum = 0;
+		if(total <= TUN_STAGE && obase + total <= td.size && !(tl.tile*TUN_TILE + TUN_TILE >= td.csize)) {
+			// common case: the tile's words are assembled in shared memory, then written with coalesced stores
+			uint32_t o = off;
 #pragma unroll
-		for(int j = 0; j < 8; j++) {
-			const uint32_t i = i0 + j;
-			if(i >= td.csize) break;
-			const uint32_t e = s_entry[by[j]];
-			const uint32_t st = e & 0xffffu;
-			uint32_t len = e >> 16;
-			if(i == td.csize - 1) len = o < td.size ? (uint32_t)(td.size - o) : 0;   // last byte: the remainder
-			for(uint32_t k = 0; k < len && o + k < td.size; k++) out[o + k] = s_text[(st + k) & (TUN_TABLE_BYTES - 1)];
-			o += len;
+			for(int j = 0; j < 8; j++) {
+				const uint32_t i = i0 + j;
+				if(i >= td.csize) break;
+				const uint32_t e = s_entry[by[j]];
+				const uint32_t st = e & 0xffffu, len = e >> 16;
+				for(uint32_t k = 0; k < len; k++) { const uint8_t v = s_text[(st + k) & (TUN_TABLE_BYTES - 1)]; s_stage[o + k] = v; ssum += v; }
+				o += len;
+			}
+			__syncthreads();
+			for(uint32_t i = tid; i < total; i += 256) out[obase + i] = s_stage[i];
+		} else {
+			// long words, the last tile of a block (its last byte is clipped, tunstall.cpp:446-451) or a corrupt stream: direct stores
+			uint64_t o = obase + off;
+#pragma unroll
+			for(int j = 0; j < 8; j++) {
+				const uint32_t i = i0 + j;
+				if(i >= td.csize) break;
+				const uint32_t e = s_entry[by[j]];
+				const uint32_t st = e & 0xffffu;
+				uint32_t len = e >> 16;
+				if(i == td.csize - 1) len = o < td.size ? (uint32_t)(td.size - o) : 0;   // last byte: the remainder
+				for(uint32_t k = 0; k < len && o + k < td.size; k++) { const uint8_t v = s_text[(st + k) & (TUN_TABLE_BYTES - 1)]; out[o + k] = v; ssum += v; }
+				o += len;
+			}
 		}
+#pragma unroll
+		for(int d = 16; d; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+		if((tid & 31) == 0 && ssum) atomicAdd(B.tun_bits + tl.a, (unsigned long long)ssum);
 		__syncthreads();   // everyone done with s_entry/s_text before the next TMA overwrites them
 	}
 }
@@ -1099,6 +1149,206 @@ __global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile 
 }
 
 // =========================================================================================================
+// K3c  point clouds, fused: bit unpack -> running delta -> dequantise -> output in ONE pass; only logs and bits are read,
+//      only final arrays are written (the unfused path moved ~60 B/vertex of int32 intermediates for a 12 B/vertex position
+//      array).  Tile = 1024 vertices of one attribute, ALL its components.  Chains (decoupled look-back, 8 state words / tile):
+//        slots 0..3  bit offset per log stream (CORRELATED / normals: one stream; decodeValues: one per component, whose base
+//                    inside the shared BITS block is the bit total of the earlier streams, summed up by k_tun_decode)
+//        slots 4..7  running sum per component (cloud delta v[i] += v[i-N]: vertex_attribute.h:177-181, normal_attribute.cpp:202-207)
+// =========================================================================================================
+template <int NC> __device__ __forceinline__ void cta_scan_multi(const uint32_t (&v)[NC], uint32_t (&excl)[NC], uint32_t (&total)[NC], uint32_t (*s_w)[9]) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc[NC];
+#pragma unroll
+	for(int k = 0; k < NC; k++) {
+		inc[k] = v[k];
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc[k], d); if(lane >= d) inc[k] += o; }
+		if(lane == 31) s_w[k][w] = inc[k];
+	}
+	__syncthreads();
+	if(w == 0) {
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			const uint32_t x = lane < 8 ? s_w[k][lane] : 0;
+			uint32_t xi = x;
+#pragma unroll
+			for(int d = 1; d < 8; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, xi, d); if(lane >= d) xi += o; }
+			if(lane < 8) s_w[k][lane] = xi - x;
+			if(lane == 7) s_w[k][8] = xi;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for(int k = 0; k < NC; k++) { excl[k] = s_w[k][w] + inc[k] - v[k]; total[k] = s_w[k][8]; }
+	__syncthreads();
+}
+
+template <int NC>
+__device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M, const AttrDesc *A, const Tile &tl, uint32_t tile_id, uint64_t *states,
+                                           uint32_t (*s_w)[9], uint64_t *s_base, uint8_t *s_out) {
+	const int tid = threadIdx.x;
+	const uint32_t nvert = M->nvert;
+	const bool correlated = (A->codec == CODEC_NORMAL) || (A->codec == CODEC_GENERIC && (A->strategy & S_CORRELATED));
+	const uint32_t i0 = tl.tile*1024u + tid*4u;
+	const uint32_t *words = (const uint32_t *)(B.blobs + A->bits_off);
+	const uint32_t nwords = A->bits_nwords;
+	const bool first = tl.first != 0;
+	// ---- logs and bit counts per stream ----
+	uint32_t d[NC][4], bits[NC];
+	uint64_t sbase[NC];                              // first bit of each stream inside the BITS block
+	{
+		uint64_t acc = 0;
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			if(correlated && k > 0) {
+#pragma unroll
+				for(int j = 0; j < 4; j++) d[k][j] = d[0][j];
+				bits[k] = 0; sbase[k] = 0;
+				continue;
+			}
+			const TunDesc td = B.tun[A->tun[k]];
+			const uint8_t *logs = B.symbols + td.out_off;
+			if(i0 + 3 < td.size) { const uchar4 q = *(const uchar4 *)(logs + i0); d[k][0] = q.x; d[k][1] = q.y; d[k][2] = q.z; d[k][3] = q.w; }
+			else {
+#pragma unroll
+				for(int j = 0; j < 4; j++) d[k][j] = (i0 + j < td.size) ? logs[i0 + j] : 0;
+			}
+			bits[k] = d[k][0] + d[k][1] + d[k][2] + d[k][3];
+			sbase[k] = acc;
+			if(!correlated) acc += B.tun_bits[A->tun[k]];     // complete: k_tun_decode finished before this kernel started
+		}
+	}
+	if(correlated) bits[0] *= (uint32_t)NC;
+	uint32_t bexcl[NC], btot[NC];
+	cta_scan_multi<NC>(bits, bexcl, btot, s_w);
+	if(tid < (correlated ? 1 : NC)) s_base[tid] = lookback_strided(states, tile_id, 8, (uint32_t)tid, first, btot[tid]);
+	__syncthreads();
+	// ---- unpack the residuals of my 4 vertices ----
+	uint32_t r[NC][4];
+	if(correlated) {
+		uint64_t pos = s_base[0] + bexcl[0];
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			const int dd = (int)d[0][j], rd = dd > 32 ? 32 : dd;
+			const uint32_t bias = array_bias(dd);
+#pragma unroll
+			for(int k = 0; k < NC; k++) {
+				uint32_t v = 0;
+				if(dd) { v = getbits(words, nwords, pos, rd) - bias; pos += (uint64_t)dd; }
+				r[k][j] = v;
+			}
+		}
+	} else {
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			uint64_t pos = sbase[k] + s_base[k] + bexcl[k];
+#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				const int dd = (int)d[k][j], rd = dd > 32 ? 32 : dd;
+				uint32_t v = 0;
+				if(dd) { v = (uint32_t)fold_value(getbits(words, nwords, pos, rd), dd); pos += (uint64_t)dd; }
+				r[k][j] = v;
+			}
+		}
+	}
+	__syncthreads();                                 // s_base is reused below
+	// ---- running sum per component (wraps mod 2^32; colours are truncated to 8 bits at the end, which commutes) ----
+	uint32_t tsum[NC], vexcl[NC], vtot[NC];
+#pragma unroll
+	for(int k = 0; k < NC; k++) {
+#pragma unroll
+		for(int j = 0; j < 4; j++) if(i0 + j >= nvert) r[k][j] = 0;
+		r[k][1] += r[k][0]; r[k][2] += r[k][1]; r[k][3] += r[k][2];
+		tsum[k] = r[k][3];
+	}
+	cta_scan_multi<NC>(tsum, vexcl, vtot, s_w);
+	if(tid < NC) s_base[tid] = lookback_strided(states, tile_id, 8, 4u + (uint32_t)tid, first, vtot[tid]);
+	__syncthreads();
+#pragma unroll
+	for(int k = 0; k < NC; k++) {
+		const uint32_t add = (uint32_t)s_base[k] + vexcl[k];
+#pragma unroll
+		for(int j = 0; j < 4; j++) r[k][j] += add;
+	}
+	__syncthreads();
+	// ---- dequantise into shared memory, then one fully coalesced copy of the tile's slice (mesh slices start at arbitrary
+	//      multiples of the vertex stride, so per-thread vector stores would be misaligned for most meshes) ----
+	const uint32_t v_lo = tl.tile*1024u, v_hi = min(nvert, v_lo + 1024u);
+	uint32_t stride;                                 // output bytes per vertex
+	if(A->codec == CODEC_GENERIC) {
+		stride = 4u*NC;
+		uint32_t *o = (uint32_t *)s_out + (size_t)tid*4*NC;
+		const float q = A->q;
+#pragma unroll
+		for(int j = 0; j < 4; j++)
+#pragma unroll
+			for(int k = 0; k < NC; k++)
+				o[j*NC + k] = A->out_format == F_FLOAT ? __float_as_uint(f_mul(i2f((int32_t)r[k][j]), q)) : f2u_x86(f_mul(__uint2float_rn(r[k][j]), q));
+	} else if(A->codec == CODEC_NORMAL) {
+		stride = A->out_format == F_FLOAT ? 12u : 6u;
+		if constexpr(NC == 2) {
+			const int unit = f2i_x86(A->q);
+#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				float nx, ny, nz;
+				if(A->out_format == F_FLOAT) {
+					to_sphere((int32_t)r[0][j], (int32_t)r[1][j], unit, nx, ny, nz);
+					float *o = (float *)s_out + (size_t)(tid*4 + j)*3;
+					o[0] = nx; o[1] = ny; o[2] = nz;
+				} else {
+					to_sphere((int32_t)(int16_t)r[0][j], (int32_t)(int16_t)r[1][j], unit, nx, ny, nz);
+					int16_t *o = (int16_t *)s_out + (size_t)(tid*4 + j)*3;
+					o[0] = f2s_x86(f_mul(nx, 32767.0f)); o[1] = f2s_x86(f_mul(ny, 32767.0f)); o[2] = f2s_x86(f_mul(nz, 32767.0f));
+				}
+			}
+		}
+	} else {                                         // colour: YCC -> RGB, scale (color_attribute.cpp:76-95, point.h:214)
+		const int oc = A->out_components;
+		stride = (uint32_t)oc;
+#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			uint32_t c[4] = {0, 0, 0, 255};
+#pragma unroll
+			for(int k = 0; k < NC; k++) c[k] = r[k][j] & 255u;
+			const uint32_t rgb[4] = { (c[2] + c[0]) & 255u, c[0], (c[1] + c[0]) & 255u, c[3] };
+			uint8_t *o = s_out + (size_t)(tid*4 + j)*oc;
+			for(int k = 0; k < oc; k++) o[k] = (uint8_t)(rgb[k]*(uint32_t)A->qc[k]);
+		}
+	}
+	__syncthreads();
+	{
+		const uint32_t nbytes = (v_hi - v_lo)*stride;
+		uint8_t *dst = (uint8_t *)A->out_ptr + (size_t)v_lo*stride;
+		if((((uintptr_t)dst | nbytes) & 3u) == 0) {
+			const uint32_t *src32 = (const uint32_t *)s_out; uint32_t *dst32 = (uint32_t *)dst;
+			for(uint32_t i = tid; i < nbytes/4; i += 256) dst32[i] = src32[i];
+		} else for(uint32_t i = tid; i < nbytes; i += 256) dst[i] = s_out[i];
+	}
+	__syncthreads();
+}
+
+// tiles: a = mesh, b = attr, tile = block of 1024 vertices, first = first tile of the attribute
+__global__ void __launch_bounds__(256) k_cloud_fused(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
+	__shared__ uint32_t s_w[4][9];
+	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_base[4];
+	__shared__ __align__(16) uint8_t s_out[1024*16];
+	for(;;) {
+		NEXT_TILE(ticket, ntiles, s_tile)
+		const Tile tl = tiles[tile_id];
+		const MeshDesc *M = B.mesh + tl.a;
+		const AttrDesc *A = &M->attr[tl.b];
+		switch(A->ncomp) {
+		case 1: cloud_tile<1>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		case 2: cloud_tile<2>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		case 3: cloud_tile<3>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		default: cloud_tile<4>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		}
+	}
+}
+
+// =========================================================================================================
 // K7  dequantise.  tiles: a = mesh, b = attr, tile = block of SCAN_TILE vertices
 // =========================================================================================================
 __global__ void __launch_bounds__(256) k_dequant(DevBatch B, const Tile *tiles, uint32_t ntiles) {
@@ -1231,6 +1481,11 @@ int launch_csr_fill(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaS
 int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
 	if(ntiles == 0) return 0;
 	k_normal_estimate<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_cloud_fused<<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {

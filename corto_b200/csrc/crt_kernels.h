@@ -16,6 +16,7 @@ struct DevBatch {
 	const uint32_t *group_ends;
 	int32_t *status;             // per mesh: 0 or CRT_E_*
 	uint32_t *vertex_count;      // per mesh: vertices the CLERS automaton created
+	unsigned long long *tun_bits; // per entropy block: sum of its decoded symbols = bits its values occupy (zeroed per decode)
 };
 
 // Per-slot state of the CLERS automaton (v1: all in global memory).
@@ -36,5 +37,6 @@ int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint6
 int launch_csr_fill(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
 int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
 int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
+int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s);
 
 }  // namespace crtb
