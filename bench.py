@@ -46,6 +46,9 @@ def parse():
     return p.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_clers_lf per c2 mesh (profiles/r1_k_clers_lf_ncu_raw.txt: 16 meshes)
+TRAFFIC_CLERS_C2_PER_MESH = int((4.685056e6 + 71.896832e6) / 16)
+
 DEFAULT_BATCH = dict(c1=1, c2=256, c3=512, c4=512, c5=1, tarta=64)
 
 
@@ -222,12 +225,19 @@ def main():
     roof = None
     if dom:
         ach = (in_bytes + out_bytes) / (stage_ms[dom] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        kernel_of = {"clers": "k_clers_lf", "delta": "k_delta_mesh / k_delta_cloud", "cloud_fused": "k_cloud_fused", "tun_decode": "k_tun_decode",
+                     "bit_unpack": "k_bit_unpack", "normals": "k_csr_* + k_normal_estimate", "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/): measured per mesh on a 16-mesh
+        # batch of this workload, scaled to this batch; null where no capture exists for the kernel/workload pair
+        traffic = None
+        if dom == "clers" and args.workload == "c2":
+            traffic = TRAFFIC_CLERS_C2_PER_MESH * batch
+        roof = {"bound": "hbm", "kernel": kernel_of.get(dom, dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
                 "algorithmic_bytes": {"blobs": in_bytes, "outputs": out_bytes},
                 "step_achieved": (in_bytes + out_bytes) * args.steps / (ms * 1e-3) / 1e9,
                 "read_only_frac": in_bytes / (stage_ms[dom] * 1e-3) / 1e9 / peak,
-                "note": "latency-bound serial CLERS automaton dominates mesh decode; see DESIGN.md"}
+                "note": "mesh decode is bound by the serial CLERS automaton (instruction latency, not HBM); see DESIGN.md section 5"}
     launches = bd.launches * args.steps
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------------
