@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tile
 //     (decodeValues: component c's bits follow component c-1's in the same BITS, cstream.h:294-319).
 // =========================================================================================================
 __global__ void __launch_bounds__(256) k_bit_unpack(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
+	__shared__ __align__(16) int32_t s_vals[BIT_TILE*4];
 	__shared__ uint32_t s_warp[9];
 	__shared__ uint32_t s_tile;
 	__shared__ uint64_t s_base;
@@ -297,6 +298,28 @@ __global__ void __launch_bounds__(256) k_bit_unpack(DevBatch B, const Tile *tile
 		const bool as_u8 = (A->codec == CODEC_COLOR);
 		int32_t *dst32 = (int32_t *)(A->codec == CODEC_NORMAL || as_u8 ? A->work_ptr : A->out_ptr);
 		uint8_t *dst8 = (uint8_t *)A->work_ptr;
+		if(correlated && nc <= 4) {
+			// one log per vertex, nc values each: the tile's values are contiguous in the output -> assemble in shared memory,
+			// one coalesced copy (per-thread 12/8-byte pieces at arbitrary alignment would cost a sector per store)
+			int32_t *mine = s_vals + (size_t)tid*4*nc;
+#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				const int dd = (int)d[j];
+				const int rd = dd > 32 ? 32 : dd;
+				const uint32_t bias = array_bias(dd);
+				for(int k = 0; k < nc; k++) {
+					uint32_t v = 0;
+					if(dd) { v = getbits(words, nwords, pos, rd) - bias; pos += (uint64_t)dd; }
+					mine[j*nc + k] = (int32_t)v;
+				}
+			}
+			__syncthreads();
+			const uint32_t lo = tl.tile*BIT_TILE, hi = min(td.size, lo + (uint32_t)BIT_TILE);
+			int32_t *dst = dst32 + (size_t)lo*nc;
+			for(uint32_t i = tid; i < (hi - lo)*(uint32_t)nc; i += 256) dst[i] = s_vals[i];
+			__syncthreads();
+			continue;
+		}
 #pragma unroll
 		for(int j = 0; j < 4; j++) {
 			const uint32_t i = i0 + j;
