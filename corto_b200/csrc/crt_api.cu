@@ -52,7 +52,7 @@ struct crt_batch {
 	std::vector<MeshDesc> h_mesh;
 	std::vector<TunDesc> h_tun;
 	std::vector<uint32_t> h_groups;
-	std::vector<Tile> t_tun, t_bits, t_cloud, t_dequant, t_faces, t_verts, t_vscan, t_cfused;
+	std::vector<Tile> t_tun, t_bits, t_dequant, t_faces, t_verts, t_vscan, t_cfused;
 	std::vector<uint2> w_delta;
 	std::vector<uint32_t> clers_order;
 	bool any_border = false;
@@ -66,7 +66,7 @@ struct crt_batch {
 	uint8_t *d_zero = nullptr;         size_t zero_bytes = 0;       // region cleared at every decode: tickets, states, status, csr counters
 	std::vector<uint8_t> h_pinned_stage;
 	// offsets inside d_tables
-	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_cloud = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
+	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
 	       o_t_vscan = 0, o_w_delta = 0, o_order = 0, o_t_cfused = 0;
 	// offsets inside d_zero
 	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_states = 0, z_csr = 0, z_tunbits = 0;
@@ -157,7 +157,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 	const int n = (int)b->meshes.size();
 	b->h_mesh.assign(n, MeshDesc{});
 	b->h_tun.clear(); b->h_groups.clear();
-	b->t_tun.clear(); b->t_bits.clear(); b->t_cloud.clear(); b->t_dequant.clear(); b->t_faces.clear(); b->t_verts.clear(); b->t_vscan.clear(); b->t_cfused.clear();
+	b->t_tun.clear(); b->t_bits.clear(); b->t_dequant.clear(); b->t_faces.clear(); b->t_verts.clear(); b->t_vscan.clear(); b->t_cfused.clear();
 	b->w_delta.clear(); b->clers_order.clear();
 	b->any_border = false;
 	symbols_bytes = 0; work_bytes = 0; zero_csr_bytes = 0; adj_bytes = 0;
@@ -278,11 +278,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			}
 			// delta inverse
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
-				if(pm.nface) b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a));
-				else {
-					uint32_t nt = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE;
-					for(int k = 0; k < A.ncomp; k++) for(uint32_t t = 0; t < nt; t++) b->t_cloud.push_back(Tile{(uint32_t)i, (uint32_t)(a | (k << 8)), t, t == 0 ? 1u : 0u});
-				}
+				b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a));       // meshes only: clouds went through the fused kernel
 			}
 			// dequantise (normals: only DIFF goes through k_dequant; ESTIMATED/BORDER are finished by k_normal_estimate)
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
@@ -377,7 +373,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->clers.delayed = (uint32_t *)cs;
 
 	// ---- zeroed control region: tickets | status | vertex_count | look-back states | csr counters ----
-	b->n_states = b->t_tun.size() + b->t_bits.size() + b->t_cloud.size() + 2*b->t_vscan.size() + 8*b->t_cfused.size();
+	b->n_states = b->t_tun.size() + b->t_bits.size() + 2*b->t_vscan.size() + 8*b->t_cfused.size();
 	b->z_ticket = 0;
 	b->z_status = 256;
 	b->z_vcount = align_up(b->z_status + (uint64_t)n*4, 256);
@@ -420,7 +416,6 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->dir_bytes = img.size();              // MeshDesc | TunDesc | groups: the directory proper
 	b->o_t_tun = put(img, b->t_tun);
 	b->o_t_bits = put(img, b->t_bits);
-	b->o_t_cloud = put(img, b->t_cloud);
 	b->o_t_dequant = put(img, b->t_dequant);
 	b->o_t_faces = put(img, b->t_faces);
 	b->o_t_verts = put(img, b->t_verts);
@@ -507,7 +502,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	uint32_t *tickets = (uint32_t *)(b->d_zero + b->z_ticket);
 	uint64_t *states = (uint64_t *)(b->d_zero + b->z_states);
 	const Tile *t_tun = (const Tile *)(b->d_tables + b->o_t_tun), *t_bits = (const Tile *)(b->d_tables + b->o_t_bits),
-	           *t_cloud = (const Tile *)(b->d_tables + b->o_t_cloud), *t_dequant = (const Tile *)(b->d_tables + b->o_t_dequant),
+	           *t_dequant = (const Tile *)(b->d_tables + b->o_t_dequant),
 	           *t_faces = (const Tile *)(b->d_tables + b->o_t_faces), *t_verts = (const Tile *)(b->d_tables + b->o_t_verts),
 	           *t_vscan = (const Tile *)(b->d_tables + b->o_t_vscan);
 	int launches = 0;
@@ -531,8 +526,6 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
 	if((rc = mark(b, "clers", k, s))) return rc;
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
-	RUN(launch_delta_cloud(B, t_cloud, (uint32_t)b->t_cloud.size(), st, tickets + 3, b->sms, s), !b->t_cloud.empty());
-	st += b->t_cloud.size();
 	if((rc = mark(b, "delta", k, s))) return rc;
 	if(!b->t_faces.empty()) {
 		RUN(launch_csr_count(B, t_faces, (uint32_t)b->t_faces.size(), s), true);

@@ -11,7 +11,7 @@
 // k_clers        Decoder::decodeFaces              src/decoder.cpp:204-358        serial automaton, one warp / mesh
 // k_delta_mesh   GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp / (mesh, attr), lane / comp
 //                NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
-// k_delta_cloud  ... (point cloud)                 vertex_attribute.h:177-181, normal_attribute.cpp:202-207
+// k_cloud_fused  point clouds: unpack + running delta (vertex_attribute.h:177-181, normal_attribute.cpp:202-207) + dequantise
 // k_csr_count / k_scan_u32 / k_csr_fill / k_normal_estimate
 //                markBoundary, estimateNormals, computeNormals   normal_attribute.cpp:24-59, 281-325
 // k_dequant      GenericAttr::dequantize, NormalAttr::dequantize, ColorAttr::dequantize
@@ -494,6 +494,7 @@ struct SmemRings4 {
 	__device__ __forceinline__ uint32_t ldLog(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aL + ((i & LM) << 2))); return v; }
 	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const {
 		uint32_t d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & AM) << 4)));
+		(void)d;
 	}
 	__device__ __forceinline__ void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c) {
 		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aA + ((id & AM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
@@ -978,49 +979,6 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 }
 
 // =========================================================================================================
-// K5'  point-cloud delta inverse: per component running sum  v[i] += v[i-N]  == inclusive scan (wraps)
-//      Tile = SCAN_TILE vertices of one component; chain = (mesh, attr, comp).
-// =========================================================================================================
-__global__ void __launch_bounds__(256) k_delta_cloud(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
-	__shared__ uint32_t s_warp[9];
-	__shared__ uint32_t s_tile;
-	__shared__ uint64_t s_base;
-	const int tid = threadIdx.x;
-	for(;;) {
-		NEXT_TILE(ticket, ntiles, s_tile)
-		const Tile tl = tiles[tile_id];
-		const MeshDesc *M = B.mesh + tl.a;
-		const int ai = tl.b & 0xff, comp = tl.b >> 8;
-		const AttrDesc *A = &M->attr[ai];
-		const int nc = A->ncomp;
-		const uint32_t nvert = M->nvert;
-		const bool as_u8 = (A->codec == CODEC_COLOR);
-		uint32_t *v32 = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
-		uint8_t *v8 = (uint8_t *)A->work_ptr;
-		const uint32_t i0 = tl.tile*SCAN_TILE + tid*4u;
-		uint32_t x[4];
-#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			const uint32_t i = i0 + j;
-			x[j] = (i < nvert) ? (as_u8 ? (uint32_t)v8[(size_t)i*nc + comp] : v32[(size_t)i*nc + comp]) : 0u;
-		}
-		x[1] += x[0]; x[2] += x[1]; x[3] += x[2];
-		uint32_t total;
-		uint32_t off = cta_scan_excl_256(x[3], s_warp, &total);
-		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
-		__syncthreads();
-		const uint32_t add = (uint32_t)s_base + off;
-#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			const uint32_t i = i0 + j;
-			if(i >= nvert) break;
-			if(as_u8) v8[(size_t)i*nc + comp] = (uint8_t)(x[j] + add);
-			else v32[(size_t)i*nc + comp] = x[j] + add;
-		}
-	}
-}
-
-// =========================================================================================================
 // K6  normal estimation (ESTIMATED / BORDER).  The reference adds face normals to their three vertices in FACE
 //     ORDER in fp32 (normal_attribute.cpp:44-55); fp32 addition is not associative, so instead of float atomics
 //     each vertex gathers its incident faces through a CSR built here and adds them in ascending face index:
@@ -1463,7 +1421,7 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 	} else {
 		// few meshes: big rings (2 CTAs per SM);  many meshes: small rings so that more serial chains share an SM
 		uint32_t RB = 4096, RA = 2048;
-		if(nwork > (uint32_t)sms*2u) { RB = 1024; RA = 1024; }
+		if(nwork > (uint32_t)sms*4u) { RB = 1024; RA = 1024; }     // really many meshes: more chains per SM beat bigger rings
 		else if(nwork <= (uint32_t)sms) { RB = 16384; RA = 2048; }   // one mesh per SM at most: the whole shared memory for its rings
 		const size_t smem = (size_t)RB*9 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
 		static size_t configured = 0;
@@ -1479,11 +1437,6 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cudaStream_t s) {
 	if(nwork == 0) return 0;
 	k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
-	LAUNCH_CHECK(); return 0;
-}
-int launch_delta_cloud(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
-	if(ntiles == 0) return 0;
-	k_delta_cloud<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_csr_count(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
