@@ -493,8 +493,7 @@ struct SmemRings4 {
 	__device__ __forceinline__ void stLog(uint32_t i, uint32_t w) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aL + ((i & LM) << 2)), "r"(w) : "memory"); }
 	__device__ __forceinline__ uint32_t ldLog(uint32_t i) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aL + ((i & LM) << 2))); return v; }
 	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const {
-		uint32_t d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & AM) << 4)));
-		(void)d;
+		[[maybe_unused]] uint32_t d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & AM) << 4)));
 	}
 	__device__ __forceinline__ void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c) {
 		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aA + ((id & AM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
