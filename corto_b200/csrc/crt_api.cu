@@ -269,12 +269,10 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 				}
 				continue;
 			}
-			// bit-unpack tiles: chain = all component streams of the attribute
-			const bool correlated = pa.codec == CODEC_NORMAL || (pa.codec == CODEC_GENERIC && (pa.strategy & S_CORRELATED));
-			bool first = true;
-			for(int k = 0; k < A.ntun; k++) {
-				uint32_t nt = (st.blocks[k].size + BIT_TILE - 1)/BIT_TILE;
-				for(uint32_t t = 0; t < nt; t++) { b->t_bits.push_back(Tile{(uint32_t)i, (uint32_t)(a | ((correlated ? 0 : k) << 8)), t, first ? 1u : 0u}); first = false; }
+			// bit-unpack tiles (all components of 1024 vertices per tile)
+			{
+				uint32_t nt = (pm.nvert + 1023)/1024;
+				for(uint32_t t = 0; t < nt; t++) b->t_bits.push_back(Tile{(uint32_t)i, (uint32_t)a, t, t == 0 ? 1u : 0u});
 			}
 			// delta inverse
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
@@ -373,7 +371,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->clers.delayed = (uint32_t *)cs;
 
 	// ---- zeroed control region: tickets | status | vertex_count | look-back states | csr counters ----
-	b->n_states = b->t_tun.size() + b->t_bits.size() + 2*b->t_vscan.size() + 8*b->t_cfused.size();
+	b->n_states = b->t_tun.size() + 8*b->t_bits.size() + 2*b->t_vscan.size() + 8*b->t_cfused.size();
 	b->z_ticket = 0;
 	b->z_status = 256;
 	b->z_vcount = align_up(b->z_status + (uint64_t)n*4, 256);
@@ -517,8 +515,8 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
 	st += b->t_tun.size();
 	if((rc = mark(b, "tun_decode", k, s))) return rc;
-	RUN(launch_bit_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st, tickets + 1, b->sms, s), !b->t_bits.empty());
-	st += b->t_bits.size();
+	RUN(launch_mesh_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st, tickets + 1, b->sms, s), !b->t_bits.empty());
+	st += 8*b->t_bits.size();
 	if((rc = mark(b, "bit_unpack", k, s))) return rc;
 	RUN(launch_cloud_fused(B, (const Tile *)(b->d_tables + b->o_t_cfused), (uint32_t)b->t_cfused.size(), st, tickets + 6, b->sms, s), !b->t_cfused.empty());
 	st += 8*b->t_cfused.size();

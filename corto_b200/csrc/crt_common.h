@@ -16,7 +16,7 @@ constexpr int TUN_REC_BYTES = 1024 + TUN_TABLE_BYTES;   // per block: 256 packed
 
 // tile sizes of the scan-based kernels (elements per CTA iteration)
 constexpr int TUN_TILE = 2048;     // compressed bytes per tile (256 threads x 8)
-constexpr int BIT_TILE = 1024;     // logs per tile (256 threads x 4)
+constexpr int BIT_TILE = 1024;     // vertices per tile of the fused unpack kernels (256 threads x 4)
 constexpr int SCAN_TILE = 1024;    // elements per tile of the generic u32 scans
 
 enum Format { F_UINT32 = 0, F_INT32, F_UINT16, F_INT16, F_UINT8, F_INT8, F_FLOAT, F_DOUBLE };

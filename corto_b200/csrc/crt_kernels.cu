@@ -7,7 +7,8 @@
 //                + InStream::decompress NONE path  src/cstream.cpp:68-73          dictionary staged in smem by TMA
 //                                                                                 (cp.async.bulk + mbarrier); output
 //                                                                                 offset = decoupled look-back scan
-// k_bit_unpack   decodeArray / decodeValues        include/corto/cstream.h:294-360 tiles of logs; bit offset = scan
+// k_unpack_fused decodeArray / decodeValues        include/corto/cstream.h:294-360 tiles of 1024 vertices, all components;
+//                (+ cloud delta + dequantise for point clouds)                    bit offset / running sum = look-back scans
 // k_clers        Decoder::decodeFaces              src/decoder.cpp:204-358        serial automaton, one warp / mesh
 // k_delta_mesh   GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp / (mesh, attr), lane / comp
 //                NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
@@ -256,90 +257,6 @@ __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tile
 		for(int d = 16; d; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
 		if((tid & 31) == 0 && ssum) atomicAdd(B.tun_bits + tl.a, (unsigned long long)ssum);
 		__syncthreads();   // everyone done with s_entry/s_text before the next TMA overwrites them
-	}
-}
-
-// =========================================================================================================
-// K3  bit unpack.  Tile = BIT_TILE logs of one component stream.  Chain = all streams of one attribute
-//     (decodeValues: component c's bits follow component c-1's in the same BITS, cstream.h:294-319).
-// =========================================================================================================
-__global__ void __launch_bounds__(256) k_bit_unpack(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
-	__shared__ __align__(16) int32_t s_vals[BIT_TILE*4];
-	__shared__ uint32_t s_warp[9];
-	__shared__ uint32_t s_tile;
-	__shared__ uint64_t s_base;
-	const int tid = threadIdx.x;
-	for(;;) {
-		NEXT_TILE(ticket, ntiles, s_tile)
-		const Tile tl = tiles[tile_id];
-		const MeshDesc *M = B.mesh + tl.a;
-		const int ai = tl.b & 0xff, comp = tl.b >> 8;
-		const AttrDesc *A = &M->attr[ai];
-		const bool correlated = (A->codec == CODEC_NORMAL) || (A->codec == CODEC_GENERIC && (A->strategy & S_CORRELATED));
-		const TunDesc td = B.tun[A->tun[correlated ? 0 : comp]];
-		const uint8_t *logs = B.symbols + td.out_off;
-		const uint32_t i0 = tl.tile*BIT_TILE + tid*4u;
-		const int nc = A->ncomp;
-		uint32_t d[4];
-		if(i0 + 3 < td.size) { uchar4 q = *(const uchar4 *)(logs + i0); d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; }
-		else {
-#pragma unroll
-			for(int j = 0; j < 4; j++) d[j] = (i0 + j < td.size) ? logs[i0 + j] : 0;
-		}
-		const uint32_t mult = correlated ? (uint32_t)nc : 1u;
-		const uint32_t mybits = (d[0] + d[1] + d[2] + d[3])*mult;
-		uint32_t total;
-		uint32_t off = cta_scan_excl_256(mybits, s_warp, &total);
-		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
-		__syncthreads();
-		uint64_t pos = s_base + off;
-		const uint32_t *words = (const uint32_t *)(B.blobs + A->bits_off);
-		const uint32_t nwords = A->bits_nwords;
-		const bool as_u8 = (A->codec == CODEC_COLOR);
-		int32_t *dst32 = (int32_t *)(A->codec == CODEC_NORMAL || as_u8 ? A->work_ptr : A->out_ptr);
-		uint8_t *dst8 = (uint8_t *)A->work_ptr;
-		if(correlated && nc <= 4) {
-			// one log per vertex, nc values each: the tile's values are contiguous in the output -> assemble in shared memory,
-			// one coalesced copy (per-thread 12/8-byte pieces at arbitrary alignment would cost a sector per store)
-			int32_t *mine = s_vals + (size_t)tid*4*nc;
-#pragma unroll
-			for(int j = 0; j < 4; j++) {
-				const int dd = (int)d[j];
-				const int rd = dd > 32 ? 32 : dd;
-				const uint32_t bias = array_bias(dd);
-				for(int k = 0; k < nc; k++) {
-					uint32_t v = 0;
-					if(dd) { v = getbits(words, nwords, pos, rd) - bias; pos += (uint64_t)dd; }
-					mine[j*nc + k] = (int32_t)v;
-				}
-			}
-			__syncthreads();
-			const uint32_t lo = tl.tile*BIT_TILE, hi = min(td.size, lo + (uint32_t)BIT_TILE);
-			int32_t *dst = dst32 + (size_t)lo*nc;
-			for(uint32_t i = tid; i < (hi - lo)*(uint32_t)nc; i += 256) dst[i] = s_vals[i];
-			__syncthreads();
-			continue;
-		}
-#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			const uint32_t i = i0 + j;
-			if(i >= td.size) break;
-			const int dd = (int)d[j];
-			const int rd = dd > 32 ? 32 : dd;
-			if(correlated) {
-				const uint32_t bias = array_bias(dd);
-				for(int k = 0; k < nc; k++) {
-					uint32_t v = 0;
-					if(dd) { v = getbits(words, nwords, pos, rd) - bias; pos += (uint64_t)dd; }
-					dst32[(size_t)i*nc + k] = (int32_t)v;
-				}
-			} else {
-				int32_t v = 0;
-				if(dd) { v = fold_value(getbits(words, nwords, pos, rd), dd); pos += (uint64_t)dd; }
-				if(as_u8) dst8[(size_t)i*nc + comp] = (uint8_t)v;
-				else dst32[(size_t)i*nc + comp] = v;
-			}
-		}
 	}
 }
 
@@ -1164,7 +1081,7 @@ template <int NC> __device__ __forceinline__ void cta_scan_multi(const uint32_t 
 	__syncthreads();
 }
 
-template <int NC>
+template <int NC, bool MESH>
 __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M, const AttrDesc *A, const Tile &tl, uint32_t tile_id, uint64_t *states,
                                            uint32_t (*s_w)[9], uint64_t *s_base, uint8_t *s_out) {
 	const int tid = threadIdx.x;
@@ -1233,6 +1150,34 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 		}
 	}
 	__syncthreads();                                 // s_base is reused below
+	const uint32_t v_lo = tl.tile*1024u, v_hi = min(nvert, v_lo + 1024u);
+	if constexpr(MESH) {
+		// meshes: the residuals themselves are the product (the delta inverse needs the topology): int32 into the attribute's
+		// output slice (generic; converted in place later, like the reference) or into scratch (normals int32, colours u8)
+		const bool as_u8 = A->codec == CODEC_COLOR;
+		const uint32_t stride = as_u8 ? (uint32_t)NC : 4u*NC;
+		if(as_u8) {
+			uint8_t *o = s_out + (size_t)tid*4*NC;
+#pragma unroll
+			for(int j = 0; j < 4; j++)
+#pragma unroll
+				for(int k = 0; k < NC; k++) o[j*NC + k] = (uint8_t)r[k][j];
+		} else {
+			uint32_t *o = (uint32_t *)s_out + (size_t)tid*4*NC;
+#pragma unroll
+			for(int j = 0; j < 4; j++)
+#pragma unroll
+				for(int k = 0; k < NC; k++) o[j*NC + k] = r[k][j];
+		}
+		__syncthreads();
+		const uint32_t nbytes = (v_hi - v_lo)*stride;
+		uint8_t *dst = (uint8_t *)((A->codec == CODEC_GENERIC) ? A->out_ptr : A->work_ptr) + (size_t)v_lo*stride;
+		if((((uintptr_t)dst | nbytes) & 3u) == 0) {
+			const uint32_t *src32 = (const uint32_t *)s_out; uint32_t *dst32 = (uint32_t *)dst;
+			for(uint32_t i = tid; i < nbytes/4; i += 256) dst32[i] = src32[i];
+		} else for(uint32_t i = tid; i < nbytes; i += 256) dst[i] = s_out[i];
+		__syncthreads();
+	} else {
 	// ---- running sum per component (wraps mod 2^32; colours are truncated to 8 bits at the end, which commutes) ----
 	uint32_t tsum[NC], vexcl[NC], vtot[NC];
 #pragma unroll
@@ -1254,7 +1199,6 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 	__syncthreads();
 	// ---- dequantise into shared memory, then one fully coalesced copy of the tile's slice (mesh slices start at arbitrary
 	//      multiples of the vertex stride, so per-thread vector stores would be misaligned for most meshes) ----
-	const uint32_t v_lo = tl.tile*1024u, v_hi = min(nvert, v_lo + 1024u);
 	uint32_t stride;                                 // output bytes per vertex
 	if(A->codec == CODEC_GENERIC) {
 		stride = 4u*NC;
@@ -1306,10 +1250,12 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 		} else for(uint32_t i = tid; i < nbytes; i += 256) dst[i] = s_out[i];
 	}
 	__syncthreads();
+	}   // point clouds
 }
 
 // tiles: a = mesh, b = attr, tile = block of 1024 vertices, first = first tile of the attribute
-__global__ void __launch_bounds__(256) k_cloud_fused(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
+template <bool MESH>
+__global__ void __launch_bounds__(256) k_unpack_fused(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
 	__shared__ uint32_t s_w[4][9];
 	__shared__ uint32_t s_tile;
 	__shared__ uint64_t s_base[4];
@@ -1320,10 +1266,10 @@ __global__ void __launch_bounds__(256) k_cloud_fused(DevBatch B, const Tile *til
 		const MeshDesc *M = B.mesh + tl.a;
 		const AttrDesc *A = &M->attr[tl.b];
 		switch(A->ncomp) {
-		case 1: cloud_tile<1>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
-		case 2: cloud_tile<2>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
-		case 3: cloud_tile<3>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
-		default: cloud_tile<4>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		case 1: cloud_tile<1, MESH>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		case 2: cloud_tile<2, MESH>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		case 3: cloud_tile<3, MESH>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
+		default: cloud_tile<4, MESH>(B, M, A, tl, tile_id, states, s_w, s_base, s_out); break;
 		}
 	}
 }
@@ -1396,11 +1342,6 @@ int launch_tun_decode(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 	k_tun_decode<<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_bit_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
-	if(ntiles == 0) return 0;
-	k_bit_unpack<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
-	LAUNCH_CHECK(); return 0;
-}
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
 	static int mode = -1;                 // CORTO_CLERS=1w selects the single-warp machine (clers_run); default: leader / follower
@@ -1460,7 +1401,12 @@ int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles
 }
 int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_cloud_fused<<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	k_unpack_fused<false><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	LAUNCH_CHECK(); return 0;
+}
+int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+	if(ntiles == 0) return 0;
+	k_unpack_fused<true><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
