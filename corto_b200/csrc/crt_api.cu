@@ -64,7 +64,6 @@ struct crt_batch {
 	std::vector<uint8_t> h_tables;
 	uint8_t *d_scratch = nullptr;      size_t scratch_bytes = 0;    // symbols, per-mesh work, dictionaries, CLERS slots
 	uint8_t *d_zero = nullptr;         size_t zero_bytes = 0;       // region cleared at every decode: tickets, states, status, csr counters
-	std::vector<uint8_t> h_pinned_stage;
 	// offsets inside d_tables
 	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
 	       o_t_vscan = 0, o_w_delta = 0, o_order = 0, o_t_cfused = 0;
@@ -145,7 +144,7 @@ extern "C" int crt_batch_mesh_info(const crt_batch *b, int i, uint32_t *nvert, u
 
 extern "C" int crt_batch_bind(crt_batch *b, const char *name, void *device_ptr, int format, int components) {
 	if(!name) return fail(CRT_E_ARG, "null attribute name");
-	if(!device_ptr) { b->binds.erase(name); b->uploaded = b->uploaded && false; return CRT_OK; }
+	if(!device_ptr) { b->binds.erase(name); return CRT_OK; }      // unbind: takes effect at the next crt_batch_upload / rewalk
 	b->binds[name] = Binding{device_ptr, format, components};
 	return CRT_OK;
 }

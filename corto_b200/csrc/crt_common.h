@@ -85,7 +85,7 @@ struct MeshDesc {
 // look-back chain (a chain = one Tunstall block / all component streams of one attribute / one scan segment).
 struct Tile {
 	uint32_t a;       // kernel-specific: TunDesc index | mesh index
-	uint32_t b;       // kernel-specific: attr | (comp << 8)
+	uint32_t b;       // kernel-specific: attribute index
 	uint32_t tile;    // tile index inside the stream
 	uint32_t first;   // 1: no predecessor in the chain
 };

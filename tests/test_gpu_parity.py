@@ -94,3 +94,28 @@ def test_tarta():
     for k, w in want.items():
         if isinstance(w, np.ndarray):
             _same("tarta/" + k, got[k], w)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_alternative_clers_machines(mode, tmp_path):
+    """CORTO_CLERS=1 (single-warp lazy-front machine) and =2 (leader/follower without window steps) stay bit-exact: they are the
+    A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "alt.py"
+    script.write_text('''
+import sys, os, glob
+sys.path.insert(0, %r)
+import numpy as np, corto_b200
+from oracle import pyoracle, refshim
+for path in sorted(glob.glob(os.path.join(%r, "*.crt"))):
+    blob = refshim.aligned_blob(open(path, "rb").read())
+    want = pyoracle.decode(blob); got = corto_b200.Decoder(blob).decode()
+    for k, w in want.items():
+        if isinstance(w, np.ndarray):
+            assert np.array_equal(got[k].view(np.uint8).reshape(-1), w.view(np.uint8).reshape(-1)), (path, k)
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")))
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, CORTO_CLERS=mode), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
