@@ -293,9 +293,9 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			if(M.attr[M.position_attr].out_format != CRT_FLOAT || !M.attr[M.position_attr].out_ptr)
 				return fail(CRT_E_NOPOSITION, "ESTIMATED/BORDER normals need the position attribute bound as float (normal_attribute.cpp:230)");
 			csr_off[i] = zero_csr_bytes;
-			zero_csr_bytes += align_up(((uint64_t)pm.nvert*4 + 2)*4, 16);
+			zero_csr_bytes += align_up(((uint64_t)pm.nvert*3 + 2)*4, 16);      // cnt | bnd | cidx[+1] | novf
 			adj_off[i] = adj_bytes;
-			adj_bytes += align_up((uint64_t)pm.nface*12, 16);
+			adj_bytes += align_up((uint64_t)pm.nvert*32 + (uint64_t)pm.nface*24, 16);   // 8 slots per vertex + overflow pairs
 			uint32_t nf = (pm.nface + SCAN_TILE - 1)/SCAN_TILE, nv = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE, ns = (pm.nvert + 1 + SCAN_TILE - 1)/SCAN_TILE;
 			for(uint32_t t = 0; t < nf; t++) b->t_faces.push_back(Tile{(uint32_t)i, 0, t, 0});
 			for(uint32_t t = 0; t < nv; t++) b->t_verts.push_back(Tile{(uint32_t)i, 0, t, 0});
@@ -370,7 +370,7 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->clers.delayed = (uint32_t *)cs;
 
 	// ---- zeroed control region: tickets | status | vertex_count | look-back states | csr counters ----
-	b->n_states = b->t_tun.size() + 8*b->t_bits.size() + 2*b->t_vscan.size() + 8*b->t_cfused.size();
+	b->n_states = b->t_tun.size() + 8*b->t_bits.size() + b->t_vscan.size() + 8*b->t_cfused.size();
 	b->z_ticket = 0;
 	b->z_status = 256;
 	b->z_vcount = align_up(b->z_status + (uint64_t)n*4, 256);
@@ -525,11 +525,9 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
 	if((rc = mark(b, "delta", k, s))) return rc;
 	if(!b->t_faces.empty()) {
-		RUN(launch_csr_count(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
-		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, 0, b->sms, s), true);
+		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
+		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
 		st += b->t_vscan.size();
-		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 5, 1, b->sms, s), b->any_border);
-		RUN(launch_csr_fill(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
 		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
 	}
 	if((rc = mark(b, "normals", k, s))) return rc;

@@ -13,7 +13,7 @@
 // k_delta_mesh   GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp / (mesh, attr), lane / comp
 //                NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
 // k_cloud_fused  point clouds: unpack + running delta (vertex_attribute.h:177-181, normal_attribute.cpp:202-207) + dequantise
-// k_csr_count / k_scan_u32 / k_csr_fill / k_normal_estimate
+// k_adj_build / k_scan_u32 / k_normal_estimate
 //                markBoundary, estimateNormals, computeNormals   normal_attribute.cpp:24-59, 281-325
 // k_dequant      GenericAttr::dequantize, NormalAttr::dequantize, ColorAttr::dequantize
 //                vertex_attribute.h:184-230, normal_attribute.cpp:257-279, color_attribute.cpp:76-95
@@ -897,19 +897,21 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 // =========================================================================================================
 // K6  normal estimation (ESTIMATED / BORDER).  The reference adds face normals to their three vertices in FACE
 //     ORDER in fp32 (normal_attribute.cpp:44-55); fp32 addition is not associative, so instead of float atomics
-//     each vertex gathers its incident faces through a CSR built here and adds them in ascending face index:
-//     bit-identical to the sequential loop for every input, no exactness guard needed.
-//     csr scratch per mesh (u32 words, zeroed per decode): deg[nvert+1] | cur[nvert] | bnd[nvert] | cidx[nvert+1];  adj[3*nface] apart
+//     each vertex gathers its incident faces and adds them in ascending face index: bit-identical to the sequential
+//     loop for every input, no exactness guard needed.  Adjacency = 8 slots per vertex filled with one atomic per face
+//     corner (one pass over the faces), the rare vertex of higher valence spills (vertex, face) pairs to an overflow list.
+//     zeroed scratch per mesh (u32): cnt[nvert] | bnd[nvert] | cidx[nvert+1] | novf;   plain scratch: adj8[8*nvert] | ovf[3*nface] (uint2)
 // =========================================================================================================
-struct CsrView { uint32_t *deg, *cur, *bnd, *cidx, *adj; };
-__device__ __forceinline__ CsrView csr_view(const MeshDesc *M) {
-	CsrView c;
+struct AdjView { uint32_t *cnt, *bnd, *cidx, *novf, *adj8; uint2 *ovf; };
+__device__ __forceinline__ AdjView adj_view(const MeshDesc *M) {
+	AdjView c;
 	uint32_t *p = (uint32_t *)M->csr_ptr;
-	c.deg = p; p += M->nvert + 1;
-	c.cur = p; p += M->nvert;
+	c.cnt = p; p += M->nvert;
 	c.bnd = p; p += M->nvert;
-	c.cidx = p;
-	c.adj = (uint32_t *)M->adj_ptr;
+	c.cidx = p; p += M->nvert + 1;
+	c.novf = p;
+	c.adj8 = (uint32_t *)M->adj_ptr;
+	c.ovf = (uint2 *)(c.adj8 + (size_t)M->nvert*8);
 	return c;
 }
 __device__ __forceinline__ void load_face(const MeshDesc *M, uint32_t f, uint32_t &a, uint32_t &b, uint32_t &c) {
@@ -918,24 +920,29 @@ __device__ __forceinline__ void load_face(const MeshDesc *M, uint32_t f, uint32_
 }
 
 // tiles: a = mesh, tile = block of SCAN_TILE faces
-__global__ void __launch_bounds__(256) k_csr_count(DevBatch B, const Tile *tiles, uint32_t ntiles) {
+__global__ void __launch_bounds__(256) k_adj_build(DevBatch B, const Tile *tiles, uint32_t ntiles) {
 	const Tile tl = tiles[blockIdx.x];
 	const MeshDesc *M = B.mesh + tl.a;
 	if(B.status[tl.a]) return;
-	const CsrView C = csr_view(M);
+	const AdjView C = adj_view(M);
 	const bool border = M->attr[M->normal_attr].prediction == N_BORDER;
 	for(uint32_t f = tl.tile*SCAN_TILE + threadIdx.x; f < min(M->nface, (tl.tile + 1)*SCAN_TILE); f += 256) {
-		uint32_t a, b, c;
-		load_face(M, f, a, b, c);
-		if(a >= M->nvert || b >= M->nvert || c >= M->nvert) continue;
-		atomicAdd(C.deg + a, 1u); atomicAdd(C.deg + b, 1u); atomicAdd(C.deg + c, 1u);
-		if(border) { atomicXor(C.bnd + a, b ^ c); atomicXor(C.bnd + b, c ^ a); atomicXor(C.bnd + c, a ^ b); }   // markBoundary :24-37
+		uint32_t v[3];
+		load_face(M, f, v[0], v[1], v[2]);
+		if(v[0] >= M->nvert || v[1] >= M->nvert || v[2] >= M->nvert) continue;
+#pragma unroll
+		for(int k = 0; k < 3; k++) {
+			const uint32_t s = atomicAdd(C.cnt + v[k], 1u);
+			if(s < 8) C.adj8[(size_t)v[k]*8 + s] = f;
+			else C.ovf[atomicAdd(C.novf, 1u)] = make_uint2(v[k], f);
+		}
+		if(border) { atomicXor(C.bnd + v[0], v[1] ^ v[2]); atomicXor(C.bnd + v[1], v[2] ^ v[0]); atomicXor(C.bnd + v[2], v[0] ^ v[1]); }   // markBoundary :24-37
 	}
 }
 
-// generic exclusive scan of u32 per mesh over nvert+1 elements (element nvert counts 0, so slot nvert receives the
-// total).  mode 0: deg -> deg in place;  mode 1: (bnd != 0) -> cidx.  tiles cover nvert+1 elements.
-__global__ void __launch_bounds__(256) k_scan_u32(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int mode) {
+// exclusive scan of the boundary flags (bnd != 0) per mesh over nvert+1 elements -> cidx: the running `count` of
+// computeNormals (normal_attribute.cpp:284-293) that indexes the BORDER diffs.  tiles cover nvert+1 elements.
+__global__ void __launch_bounds__(256) k_scan_u32(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
 	__shared__ uint32_t s_warp[9];
 	__shared__ uint32_t s_tile;
 	__shared__ uint64_t s_base;
@@ -944,36 +951,21 @@ __global__ void __launch_bounds__(256) k_scan_u32(DevBatch B, const Tile *tiles,
 		NEXT_TILE(ticket, ntiles, s_tile)
 		const Tile tl = tiles[tile_id];
 		const MeshDesc *M = B.mesh + tl.a;
-		const CsrView C = csr_view(M);
+		const AdjView C = adj_view(M);
 		const uint32_t n = M->nvert;
 		const uint32_t i0 = tl.tile*SCAN_TILE + tid*4u;
 		uint32_t x[4];
 #pragma unroll
-		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; x[j] = (i < n) ? (mode == 0 ? C.deg[i] : (C.bnd[i] != 0u ? 1u : 0u)) : 0u; }
+		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; x[j] = (i < n && C.bnd[i] != 0u) ? 1u : 0u; }
 		const uint32_t s1 = x[0], s2 = s1 + x[1], s3 = s2 + x[2], s4 = s3 + x[3];
 		uint32_t total;
 		uint32_t off = cta_scan_excl_256(s4, s_warp, &total);
 		if(tid == 0) s_base = lookback(states, tile_id, tl.first != 0, total);
 		__syncthreads();
 		const uint32_t base = (uint32_t)s_base + off;
-		uint32_t *dst = mode == 0 ? C.deg : C.cidx;
 		const uint32_t e[4] = { base, base + s1, base + s2, base + s3 };
 #pragma unroll
-		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; if(i <= n) dst[i] = e[j]; }
-	}
-}
-
-__global__ void __launch_bounds__(256) k_csr_fill(DevBatch B, const Tile *tiles, uint32_t ntiles) {
-	const Tile tl = tiles[blockIdx.x];
-	const MeshDesc *M = B.mesh + tl.a;
-	if(B.status[tl.a]) return;
-	const CsrView C = csr_view(M);
-	for(uint32_t f = tl.tile*SCAN_TILE + threadIdx.x; f < min(M->nface, (tl.tile + 1)*SCAN_TILE); f += 256) {
-		uint32_t v[3];
-		load_face(M, f, v[0], v[1], v[2]);
-		if(v[0] >= M->nvert || v[1] >= M->nvert || v[2] >= M->nvert) continue;
-#pragma unroll
-		for(int k = 0; k < 3; k++) { const uint32_t s = C.deg[v[k]] + atomicAdd(C.cur + v[k], 1u); C.adj[s] = f; }
+		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; if(i <= n) C.cidx[i] = e[j]; }
 	}
 }
 
@@ -982,36 +974,69 @@ __global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile 
 	const Tile tl = tiles[blockIdx.x];
 	const MeshDesc *M = B.mesh + tl.a;
 	if(B.status[tl.a]) return;
-	const CsrView C = csr_view(M);
+	const AdjView C = adj_view(M);
 	const AttrDesc *A = &M->attr[M->normal_attr];
 	const int32_t *P = (const int32_t *)M->attr[M->position_attr].out_ptr;   // still integer (decoder.cpp:191-195)
 	const int32_t *diffs = (const int32_t *)A->work_ptr;
 	const int unit = f2i_x86(A->q);
 	const bool border = A->prediction == N_BORDER;
 	for(uint32_t i = tl.tile*SCAN_TILE + threadIdx.x; i < min(M->nvert, (tl.tile + 1)*SCAN_TILE); i += 256) {
-		const uint32_t beg = C.deg[i], end = C.deg[i + 1];
+		const uint32_t deg = C.cnt[i];
 		float ex = 0.f, ey = 0.f, ez = 0.f;
-		// incident faces in ascending face index: repeated "smallest face id greater than the last one"
-		uint32_t done = 0;
-		int64_t last = -1;
-		while(done < end - beg) {
-			uint32_t fmin = 0xffffffffu, mult = 0;
-			for(uint32_t s = beg; s < end; s++) {
-				const uint32_t f = C.adj[s];
-				if((int64_t)f > last) { if(f < fmin) { fmin = f; mult = 1; } else if(f == fmin) mult++; }
-			}
-			if(mult == 0) break;
+		auto add_face = [&](uint32_t f) {                              // estimateNormals :44-55, one corner's worth
 			uint32_t a, b, c;
-			load_face(M, fmin, a, b, c);
+			load_face(M, f, a, b, c);
 			const float v0x = i2f(P[(size_t)a*3]), v0y = i2f(P[(size_t)a*3 + 1]), v0z = i2f(P[(size_t)a*3 + 2]);
 			const float ax = f_sub(i2f(P[(size_t)b*3]), v0x), ay = f_sub(i2f(P[(size_t)b*3 + 1]), v0y), az = f_sub(i2f(P[(size_t)b*3 + 2]), v0z);
 			const float bx = f_sub(i2f(P[(size_t)c*3]), v0x), by = f_sub(i2f(P[(size_t)c*3 + 1]), v0y), bz = f_sub(i2f(P[(size_t)c*3 + 2]), v0z);
-			const float nx = f_sub(f_mul(ay, bz), f_mul(az, by));       // point.h:113-115
-			const float ny = f_sub(f_mul(az, bx), f_mul(ax, bz));
-			const float nz = f_sub(f_mul(ax, by), f_mul(ay, bx));
-			for(uint32_t m = 0; m < mult; m++) { ex = f_add(ex, nx); ey = f_add(ey, ny); ez = f_add(ez, nz); }
-			done += mult;
-			last = (int64_t)fmin;
+			ex = f_add(ex, f_sub(f_mul(ay, bz), f_mul(az, by)));      // point.h:113-115
+			ey = f_add(ey, f_sub(f_mul(az, bx), f_mul(ax, bz)));
+			ez = f_add(ez, f_sub(f_mul(ax, by), f_mul(ay, bx)));
+		};
+		if(deg <= 8) {
+			// the usual case: sort the (at most 8) incident faces in registers, add in ascending face order
+			const uint4 q0 = *(const uint4 *)(C.adj8 + (size_t)i*8), q1 = *(const uint4 *)(C.adj8 + (size_t)i*8 + 4);
+			uint32_t f0 = deg > 0 ? q0.x : 0xffffffffu, f1 = deg > 1 ? q0.y : 0xffffffffu, f2 = deg > 2 ? q0.z : 0xffffffffu, f3 = deg > 3 ? q0.w : 0xffffffffu;
+			uint32_t f4 = deg > 4 ? q1.x : 0xffffffffu, f5 = deg > 5 ? q1.y : 0xffffffffu, f6 = deg > 6 ? q1.z : 0xffffffffu, f7 = deg > 7 ? q1.w : 0xffffffffu;
+#define CRT_CE(a, b) { const uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+			CRT_CE(f0, f1) CRT_CE(f2, f3) CRT_CE(f4, f5) CRT_CE(f6, f7)
+			CRT_CE(f0, f2) CRT_CE(f1, f3) CRT_CE(f4, f6) CRT_CE(f5, f7)
+			CRT_CE(f1, f2) CRT_CE(f5, f6) CRT_CE(f0, f4) CRT_CE(f3, f7)
+			CRT_CE(f1, f5) CRT_CE(f2, f6)
+			CRT_CE(f1, f4) CRT_CE(f3, f6)
+			CRT_CE(f2, f4) CRT_CE(f3, f5)
+			CRT_CE(f3, f4)
+#undef CRT_CE
+			if(deg > 0) add_face(f0);
+			if(deg > 1) add_face(f1);
+			if(deg > 2) add_face(f2);
+			if(deg > 3) add_face(f3);
+			if(deg > 4) add_face(f4);
+			if(deg > 5) add_face(f5);
+			if(deg > 6) add_face(f6);
+			if(deg > 7) add_face(f7);
+		} else {
+			// high valence (fan poles): repeated "smallest face id greater than the last one" over the 8 slots + this vertex's
+			// entries of the overflow list; a face naming the vertex twice is added twice, like the reference's corner loop
+			const uint32_t novf = *C.novf;
+			uint32_t done = 0;
+			int64_t last = -1;
+			while(done < deg) {
+				uint32_t fmin = 0xffffffffu, mult = 0;
+				for(uint32_t s = 0; s < 8; s++) {
+					const uint32_t f = C.adj8[(size_t)i*8 + s];
+					if((int64_t)f > last) { if(f < fmin) { fmin = f; mult = 1; } else if(f == fmin) mult++; }
+				}
+				for(uint32_t s = 0; s < novf; s++) {
+					const uint2 e = C.ovf[s];
+					if(e.x != i) continue;
+					if((int64_t)e.y > last) { if(e.y < fmin) { fmin = e.y; mult = 1; } else if(e.y == fmin) mult++; }
+				}
+				if(mult == 0) break;
+				for(uint32_t m = 0; m < mult; m++) add_face(fmin);
+				done += mult;
+				last = (int64_t)fmin;
+			}
 		}
 		if(!border || C.bnd[i] != 0u) {                               // computeNormals :288-293 / :315-319
 			int32_t qx, qy;
@@ -1078,7 +1103,7 @@ template <int NC> __device__ __forceinline__ void cta_scan_multi(const uint32_t 
 	__syncthreads();
 #pragma unroll
 	for(int k = 0; k < NC; k++) { excl[k] = s_w[k][w] + inc[k] - v[k]; total[k] = s_w[k][8]; }
-	__syncthreads();
+	// no trailing barrier: every caller has a __syncthreads between these reads of s_w and its next use of the scan
 }
 
 template <int NC, bool MESH>
@@ -1149,7 +1174,6 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 			}
 		}
 	}
-	__syncthreads();                                 // s_base is reused below
 	const uint32_t v_lo = tl.tile*1024u, v_hi = min(nvert, v_lo + 1024u);
 	if constexpr(MESH) {
 		// meshes: the residuals themselves are the product (the delta inverse needs the topology): int32 into the attribute's
@@ -1176,8 +1200,9 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 			const uint32_t *src32 = (const uint32_t *)s_out; uint32_t *dst32 = (uint32_t *)dst;
 			for(uint32_t i = tid; i < nbytes/4; i += 256) dst32[i] = src32[i];
 		} else for(uint32_t i = tid; i < nbytes; i += 256) dst[i] = s_out[i];
-		__syncthreads();
+		// (the next tile touches s_out / s_base only after the two barriers of NEXT_TILE)
 	} else {
+	__syncthreads();                                 // s_base is reused below
 	// ---- running sum per component (wraps mod 2^32; colours are truncated to 8 bits at the end, which commutes) ----
 	uint32_t tsum[NC], vexcl[NC], vtot[NC];
 #pragma unroll
@@ -1249,7 +1274,6 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 			for(uint32_t i = tid; i < nbytes/4; i += 256) dst32[i] = src32[i];
 		} else for(uint32_t i = tid; i < nbytes; i += 256) dst[i] = s_out[i];
 	}
-	__syncthreads();
 	}   // point clouds
 }
 
@@ -1379,19 +1403,14 @@ int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cuda
 	k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_csr_count(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
+int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_csr_count<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	k_adj_build<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int mode, int sms, cudaStream_t s) {
+int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_scan_u32<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket, mode);
-	LAUNCH_CHECK(); return 0;
-}
-int launch_csr_fill(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
-	if(ntiles == 0) return 0;
-	k_csr_fill<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	k_scan_u32<<<persistent_grid(ntiles, 8, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
