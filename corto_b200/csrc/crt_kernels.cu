@@ -774,54 +774,99 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 // =========================================================================================================
 template <typename T, int NC>
 __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint32_t nvert, bool par, int lane) {
-	// software pipeline: the NEXT round's prediction and residuals are fetched while this round computes (they are not
-	// touched by this round), so each round pays one dependent memory round trip (the operand gather) instead of two
-	uint4 p_next = (uint32_t)lane < nvert ? pred[lane] : make_uint4(0, 0, 0, 0);
-	uint32_t x_next[NC];
+	// Two-deep software pipeline over rounds of 32 vertices:
+	//   * prediction + residuals are fetched TWO rounds ahead (they are streams nobody writes before their round);
+	//   * the operand gather of round r+1 is issued BEFORE round r is resolved, for every operand that is already final
+	//     (vertex < base_r) or a still-untouched residual (vertex beyond round r+1: hostile streams only); operands that land
+	//     inside round r are taken from round r's registers with a shuffle once it is done.
+	// So the dependent chain per round is the in-register resolution only; the L2 round trip of the gather overlaps it.
+	const uint32_t FULL = 0xffffffffu;
+	auto ldp = [&](uint32_t i) { return i < nvert ? pred[i] : make_uint4(0, 0, 0, 0); };
+	uint4 pA = ldp((uint32_t)lane), pB = ldp(32u + lane);          // round r, r+1
+	uint32_t xA[NC], xB[NC], xprev[NC];
 #pragma unroll
-	for(int k = 0; k < NC; k++) x_next[k] = (uint32_t)lane < nvert ? (uint32_t)v[(size_t)lane*NC + k] : 0u;
+	for(int k = 0; k < NC; k++) {
+		xA[k] = (uint32_t)lane < nvert ? (uint32_t)v[(size_t)lane*NC + k] : 0u;
+		xB[k] = 32u + lane < nvert ? (uint32_t)v[(size_t)(32u + lane)*NC + k] : 0u;
+		xprev[k] = 0;
+	}
+	// gathered operands of the current round + which of them wait for the previous round's registers
+	uint32_t fa[NC], fb[NC], fc[NC];
+	uint32_t pend = 0;                                               // bit0 a, bit1 b, bit2 c: operand lies in the previous round
+	{
+		// round 0 has no earlier vertices: operands are inside the block or (hostile) beyond it = residuals
+		const uint32_t i = lane;
+		const bool act = i < nvert && i > 0;
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			fa[k] = (act && pA.x >= 32u && pA.x < nvert) ? (uint32_t)v[(size_t)pA.x*NC + k] : 0u;
+			fb[k] = (act && par && pA.y >= 32u && pA.y < nvert) ? (uint32_t)v[(size_t)pA.y*NC + k] : 0u;
+			fc[k] = (act && par && pA.z >= 32u && pA.z < nvert) ? (uint32_t)v[(size_t)pA.z*NC + k] : 0u;
+		}
+	}
 	for(uint32_t base = 0; base < nvert; base += 32) {
 		const uint32_t i = base + lane;
 		const bool in = i < nvert;
 		const bool act = in && i > 0;                 // vertex 0 keeps its residual (loops start at 1)
-		const uint4 p = p_next;
-		const uint32_t a = p.x, b = p.y, c = p.z;
-		uint32_t x[NC], fa[NC], fb[NC], fc[NC];
-		const bool a_in = act && (a - base) < 32u, b_in = act && par && (b - base) < 32u, c_in = act && par && (c - base) < 32u;
-#pragma unroll
-		for(int k = 0; k < NC; k++) {
-			x[k] = x_next[k];
-			fa[k] = (act && !a_in && a < nvert) ? (uint32_t)v[(size_t)a*NC + k] : 0u;
-			fb[k] = (act && par && !b_in && b < nvert) ? (uint32_t)v[(size_t)b*NC + k] : 0u;
-			fc[k] = (act && par && !c_in && c < nvert) ? (uint32_t)v[(size_t)c*NC + k] : 0u;
-		}
+		const uint32_t a = pA.x, b = pA.y, c = pA.z;
+		// ---- operands that were inside the previous round: its final values are still in registers ----
 		{
-			// the streams read one round ahead (prediction, residuals) come from DRAM: pull them into L2 several rounds earlier
-			const uint32_t far = i + 32u*8u;
-			if(far < nvert) {
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(pred + far));
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(v + (size_t)far*NC));
-			}
-			const uint32_t in2 = i + 32;
-			p_next = in2 < nvert ? pred[in2] : make_uint4(0, 0, 0, 0);
+			const uint32_t la = (a - (base - 32u)) & 31u, lb = (b - (base - 32u)) & 31u, lc = (c - (base - 32u)) & 31u;
 #pragma unroll
-			for(int k = 0; k < NC; k++) x_next[k] = in2 < nvert ? (uint32_t)v[(size_t)in2*NC + k] : 0u;
+			for(int k = 0; k < NC; k++) {
+				const uint32_t va = __shfl_sync(FULL, xprev[k], la), vb = __shfl_sync(FULL, xprev[k], lb), vc = __shfl_sync(FULL, xprev[k], lc);
+				if(pend & 1u) fa[k] = va;
+				if(pend & 2u) fb[k] = vb;
+				if(pend & 4u) fc[k] = vc;
+			}
 		}
+		// ---- issue the gather of the NEXT round (everything that does not depend on this round) + prefetch two rounds ahead ----
+		uint32_t ga[NC], gb[NC], gc[NC], pend_n = 0;
+		{
+			const uint32_t nb = base + 32u, ni = nb + lane;
+			const bool nact = ni < nvert;                               // ni > 0 always
+			const uint32_t na = pB.x, nbb = pB.y, nc = pB.z;
+			auto far = [&](uint32_t X, bool use, uint32_t bit, uint32_t (&g)[NC]) {
+				const bool in_this = use && X - base < 32u;              // resolved from this round's registers next iteration
+				const bool in_next = use && X - nb < 32u;                // inside its own round
+				if(in_this) pend_n |= bit;
+#pragma unroll
+				for(int k = 0; k < NC; k++) g[k] = (use && !in_this && !in_next && X < nvert) ? (uint32_t)v[(size_t)X*NC + k] : 0u;
+			};
+			far(na, nact, 1u, ga); far(nbb, nact && par, 2u, gb); far(nc, nact && par, 4u, gc);
+		}
+		const uint32_t i2 = i + 64u;
+		const uint4 pC = ldp(i2);
+		uint32_t xC[NC];
+#pragma unroll
+		for(int k = 0; k < NC; k++) xC[k] = i2 < nvert ? (uint32_t)v[(size_t)i2*NC + k] : 0u;
+		{
+			const uint32_t farv = i + 32u*10u;                          // pull the streams into L2 well ahead
+			if(farv < nvert) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(pred + farv));
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(v + (size_t)farv*NC));
+			}
+		}
+		// ---- resolve this round ----
+		uint32_t x[NC];
+#pragma unroll
+		for(int k = 0; k < NC; k++) x[k] = xA[k];
+		const bool a_in = act && (a - base) < 32u, b_in = act && par && (b - base) < 32u, c_in = act && par && (c - base) < 32u;
 		// fast path: b and c outside the block, a anywhere EARLIER in the block (or outside): x_i = r_i + x_parent(i) is a forest
 		// whose parents have lower lane numbers -> pointer doubling, 5 shuffle rounds (a chain a = i-1, 99.7 % of a grid, and
 		// the strip starts in between are both covered)
 		const bool tree_ok = !act || (!b_in && !c_in && (!a_in || a < i));
-		if(__all_sync(0xffffffffu, tree_ok)) {
+		if(__all_sync(FULL, tree_ok)) {
 			uint32_t parent = a_in ? (a - base) : 0xffffffffu;     // lane of the in-block parent, or none
 			uint32_t r[NC];
 #pragma unroll
-			for(int k = 0; k < NC; k++) r[k] = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k];
+			for(int k = 0; k < NC; k++) r[k] = act ? x[k] + (a_in ? 0u : fa[k]) + fb[k] - fc[k] : x[k];
 #pragma unroll
 			for(int d = 0; d < 5; d++) {
 				const uint32_t src = parent == 0xffffffffu ? (uint32_t)lane : parent;
-				const uint32_t pp = __shfl_sync(0xffffffffu, parent, src);
+				const uint32_t pp = __shfl_sync(FULL, parent, src);
 #pragma unroll
-				for(int k = 0; k < NC; k++) { const uint32_t pr = __shfl_sync(0xffffffffu, r[k], src); if(parent != 0xffffffffu) r[k] += pr; }
+				for(int k = 0; k < NC; k++) { const uint32_t pr = __shfl_sync(FULL, r[k], src); if(parent != 0xffffffffu) r[k] += pr; }
 				if(parent != 0xffffffffu) parent = pp;
 			}
 #pragma unroll
@@ -833,21 +878,20 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 			const uint32_t la = a_in ? a - base : 64u, lb = b_in ? b - base : 64u, lc = c_in ? c - base : 64u;
 			uint32_t acc[NC], res[NC];
 #pragma unroll
-			for(int k = 0; k < NC; k++) { res[k] = x[k]; acc[k] = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k]; }
-			// operands that point at this lane or a higher one never become final before this lane: they contribute residuals
+			for(int k = 0; k < NC; k++) { res[k] = x[k]; acc[k] = act ? x[k] + (a_in ? 0u : fa[k]) + (b_in ? 0u : fb[k]) - (c_in ? 0u : fc[k]) : x[k]; }
 #pragma unroll
 			for(int k = 0; k < NC; k++) {
-				const uint32_t ra = __shfl_sync(0xffffffffu, res[k], la & 31u), rb = __shfl_sync(0xffffffffu, res[k], lb & 31u), rc = __shfl_sync(0xffffffffu, res[k], lc & 31u);
+				const uint32_t ra = __shfl_sync(FULL, res[k], la & 31u), rb = __shfl_sync(FULL, res[k], lb & 31u), rc = __shfl_sync(FULL, res[k], lc & 31u);
 				if(la < 32u && la >= (uint32_t)lane) acc[k] += ra;
 				if(lb < 32u && lb >= (uint32_t)lane) acc[k] += rb;
 				if(lc < 32u && lc >= (uint32_t)lane) acc[k] -= rc;
 			}
-			const uint32_t named = __reduce_or_sync(0xffffffffu, (la < (uint32_t)lane ? 1u << la : 0u) | (lb < (uint32_t)lane ? 1u << lb : 0u) | (lc < (uint32_t)lane ? 1u << lc : 0u));
+			const uint32_t named = __reduce_or_sync(FULL, (la < (uint32_t)lane ? 1u << la : 0u) | (lb < (uint32_t)lane ? 1u << lb : 0u) | (lc < (uint32_t)lane ? 1u << lc : 0u));
 			for(uint32_t todo = named; todo; todo &= todo - 1) {
 				const int j = __ffs(todo) - 1;             // every lane below j that anyone names has been pushed already, so acc of lane j is final
 #pragma unroll
 				for(int k = 0; k < NC; k++) {
-					const uint32_t xj = __shfl_sync(0xffffffffu, acc[k], j);
+					const uint32_t xj = __shfl_sync(FULL, acc[k], j);
 					if(la == (uint32_t)j) acc[k] += xj;
 					if(lb == (uint32_t)j) acc[k] += xj;
 					if(lc == (uint32_t)j) acc[k] -= xj;
@@ -861,6 +905,10 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 			for(int k = 0; k < NC; k++) v[(size_t)i*NC + k] = (T)x[k];
 		}
 		__syncwarp();
+		// ---- rotate the pipeline ----
+		pA = pB; pB = pC; pend = pend_n;
+#pragma unroll
+		for(int k = 0; k < NC; k++) { xprev[k] = x[k]; xA[k] = xB[k]; xB[k] = xC[k]; fa[k] = ga[k]; fb[k] = gb[k]; fc[k] = gc[k]; }
 	}
 }
 
