@@ -184,7 +184,6 @@ def main():
     bd = corto_b200.BatchDecoder(views)
     bd.allocate()
     bd.upload()
-    bd.set_profiling(True)
     for _ in range(max(args.warmup, 3)):
         bd.rewalk(); bd.decode()
     torch.cuda.synchronize()
@@ -198,13 +197,9 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    per_step_stage = []
     for _ in range(args.steps):
         bd.rewalk()          # host directory walk + H2D of the directory: part of Decoder::decode, so part of the step
         bd.decode()
-        # stage events are re-recorded every step; read them lazily after a sync of this step only when cheap
-        torch.cuda.current_stream().synchronize()
-        per_step_stage.append(bd.stage_times())
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -215,6 +210,15 @@ def main():
     ms_max = float(tms.item())
     total_verts = bd.total_verts * world
     value = total_verts * args.steps / (ms_max * 1e-3) / 1e6
+    # Per-kernel durations (roofline): the same steps once more with the stage timers on (the timed region above runs without
+    # them and without a host sync per step, so that the directory walk of step k+1 overlaps the kernels of step k).
+    bd.set_profiling(True)
+    per_step_stage = []
+    for _ in range(min(args.steps, 5)):
+        bd.rewalk(); bd.decode()
+        torch.cuda.current_stream().synchronize()
+        per_step_stage.append(bd.stage_times())
+    bd.set_profiling(False)
     for st_ in per_step_stage:
         for name, t in st_:
             stage_acc.setdefault(name, []).append(t)
@@ -236,6 +240,7 @@ def main():
                 "algorithmic_bytes": {"blobs": in_bytes, "outputs": out_bytes},
                 "step_achieved": (in_bytes + out_bytes) * args.steps / (ms * 1e-3) / 1e9,
                 "read_only_frac": in_bytes / (stage_ms[dom] * 1e-3) / 1e9 / peak,
+                "stage_ms_from": "a re-run of the same steps right after the timed region with the library's stage timers (CUDA events) on",
                 "note": "mesh decode is bound by the serial CLERS automaton (instruction latency, not HBM); see DESIGN.md section 5"}
     launches = bd.launches * args.steps
 

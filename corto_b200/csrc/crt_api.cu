@@ -80,6 +80,10 @@ struct crt_batch {
 	bool profiling = false;
 	std::vector<Stage> stages;
 	std::vector<int> h_status;
+	// intra-batch overlap: the attribute unpack runs beside the CLERS automaton, the adjacency build beside the delta inverse
+	cudaStream_t side = nullptr;
+	cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+	int overlap = -1;                  // -1: read CORTO_OVERLAP on first use
 };
 
 extern "C" crt_batch *crt_batch_create(int n, const unsigned char *const *blobs, const int *lens) {
@@ -107,6 +111,12 @@ static void batch_free_device(crt_batch *b) {
 	b->d_blobs = b->d_tables = b->d_scratch = b->d_zero = nullptr;
 	for(auto &s: b->stages) cudaEventDestroy(s.ev);
 	b->stages.clear();
+	for(int k = 0; k < 2; k++) {
+		if(b->ev_fork[k]) cudaEventDestroy(b->ev_fork[k]);
+		if(b->ev_join[k]) cudaEventDestroy(b->ev_join[k]);
+		b->ev_fork[k] = b->ev_join[k] = nullptr;
+	}
+	if(b->side) { cudaStreamDestroy(b->side); b->side = nullptr; }
 	b->uploaded = false;
 }
 
@@ -275,7 +285,8 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			}
 			// delta inverse
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
-				b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a));       // meshes only: clouds went through the fused kernel
+				for(int c = 0; c < A.ncomp; c++)                                      // one warp per component (k_delta_mesh)
+					b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a | ((unsigned)c << 8)));   // meshes only: clouds went through the fused kernel
 			}
 			// dequantise (normals: only DIFF goes through k_dequant; ESTIMATED/BORDER are finished by k_normal_estimate)
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
@@ -514,20 +525,57 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
 	st += b->t_tun.size();
 	if((rc = mark(b, "tun_decode", k, s))) return rc;
-	RUN(launch_mesh_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st, tickets + 1, b->sms, s), !b->t_bits.empty());
-	st += 8*b->t_bits.size();
+	// Stage order inside one batch.  Default: every stage on the caller's stream.  CORTO_OVERLAP (bit 0: attribute unpack beside
+	// the CLERS automaton, bit 1: adjacency build beside the delta inverse, both on a side stream) is an experiment switch: the
+	// two latency-bound kernels leave most SMs idle, but on B200 the company costs them more than it saves (measured on
+	// configs[1]: 13.1 ms with both overlaps vs 11.7 ms serial — the automaton's two warps per mesh lose issue slots and L1 to
+	// the wide kernel), so it is off unless asked for.  Stage timers (profiling) always run serial.
+	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 3 : 0; }
+	const bool ovl = (b->overlap & 1) && !b->profiling && !b->clers_order.empty() && !b->t_bits.empty();
+	const bool want2 = (b->overlap & 2) && !b->profiling && !b->t_faces.empty() && !b->w_delta.empty();
+	cudaStream_t s2 = s;
+	if(ovl || want2) {
+		if(!b->side) {
+			CU(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+			for(int k2 = 0; k2 < 2; k2++) {
+				CU(cudaEventCreateWithFlags(&b->ev_fork[k2], cudaEventDisableTiming));
+				CU(cudaEventCreateWithFlags(&b->ev_join[k2], cudaEventDisableTiming));
+			}
+		}
+	}
+	if(ovl) s2 = b->side;
+	uint64_t *st_bits = st, *st_cfused = st + 8*b->t_bits.size();
+	st = st_cfused + 8*b->t_cfused.size();
+	if(ovl) {
+		CU(cudaEventRecord(b->ev_fork[0], s));
+		RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), true);
+		CU(cudaStreamWaitEvent(s2, b->ev_fork[0], 0));
+	}
+	RUN(launch_mesh_unpack(B, t_bits, (uint32_t)b->t_bits.size(), st_bits, tickets + 1, b->sms, s2), !b->t_bits.empty());
 	if((rc = mark(b, "bit_unpack", k, s))) return rc;
-	RUN(launch_cloud_fused(B, (const Tile *)(b->d_tables + b->o_t_cfused), (uint32_t)b->t_cfused.size(), st, tickets + 6, b->sms, s), !b->t_cfused.empty());
-	st += 8*b->t_cfused.size();
+	RUN(launch_cloud_fused(B, (const Tile *)(b->d_tables + b->o_t_cfused), (uint32_t)b->t_cfused.size(), st_cfused, tickets + 6, b->sms, s2), !b->t_cfused.empty());
 	if((rc = mark(b, "cloud_fused", k, s))) return rc;
-	RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
+	if(ovl) {
+		CU(cudaEventRecord(b->ev_join[0], s2));
+		CU(cudaStreamWaitEvent(s, b->ev_join[0], 0));
+	} else {
+		RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
+	}
 	if((rc = mark(b, "clers", k, s))) return rc;
+	const bool ovl2 = want2;
+	if(ovl2) CU(cudaEventRecord(b->ev_fork[1], s));
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
 	if((rc = mark(b, "delta", k, s))) return rc;
 	if(!b->t_faces.empty()) {
-		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
-		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
+		cudaStream_t sa = ovl2 ? b->side : s;
+		if(ovl2) CU(cudaStreamWaitEvent(sa, b->ev_fork[1], 0));
+		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), sa), true);
+		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, sa), b->any_border);
 		st += b->t_vscan.size();
+		if(ovl2) {
+			CU(cudaEventRecord(b->ev_join[1], sa));
+			CU(cudaStreamWaitEvent(s, b->ev_join[1], 0));
+		}
 		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
 	}
 	if((rc = mark(b, "normals", k, s))) return rc;

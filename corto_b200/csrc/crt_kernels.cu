@@ -431,80 +431,96 @@ __device__ __forceinline__ void st_vol_shared(uint32_t *p, uint32_t v) { asm vol
 // its neighbours in the run), LEFT k consumes the k-th edge of the prev chain.  Only the prev-chain walk is serial (one
 // dependent shared-memory load per LEFT); ids, link records, flags and log words are written by 32 lanes at once.  The
 // scalar machine yields (return 3) when it sees such a run and takes over again at the first other symbol.
-// Returns the number of symbols consumed (>= 2) or 0 when the window must go through the scalar path (loop closure in
-// sight, capacity edge, run too short).  S is valid in lane 0 only.
-__device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S, uint32_t left, uint32_t *chain, uint32_t lane) {
+// One call runs window after window (32 symbols each) for as long as the run and the chunk budget last; inside the loop
+// the machine state is warp-uniform (every lane holds the same copy), so nothing is shuffled between windows.  The
+// symbols of the NEXT window are loaded as soon as the length of this one is known, so that the global-memory latency
+// hides behind the rest of the step (`pre` carries them from call to call).
+// Returns the number of symbols consumed (0: the first window must go through the scalar path — loop closure in sight,
+// capacity edge, run too short).  S is valid in lane 0 only.
+struct LeadPre { uint32_t sym, at; };    // per lane: clers[at + lane] (0xff past the end); `at` is warp-uniform
+
+__device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S, uint32_t left, uint32_t *chain, uint32_t lane, LeadPre &pre) {
 	const uint32_t FULL = 0xffffffffu;
 	__syncwarp();                                          // lane 0's scalar ring stores are visible to every lane from here
 	if(!__shfl_sync(FULL, S.have, 0)) return 0;            // no current edge: the scalar machine has to pop one first
-	const uint32_t cler = __shfl_sync(FULL, S.cler, 0), start = __shfl_sync(FULL, S.start, 0), end = __shfl_sync(FULL, S.end, 0);
-	const uint32_t nfront0 = __shfl_sync(FULL, S.nfront, 0), next0 = __shfl_sync(FULL, S.cnext, 0), nlog0 = __shfl_sync(FULL, S.nlog, 0);
-	const uint32_t eflush = __shfl_sync(FULL, S.eflush, 0);
-	uint32_t lim = min(min(32u, left), min(io.nclers - cler, end - start));
-	const uint32_t sym = lane < lim ? (uint32_t)io.clers[cler + lane] : 0xffu;
-	const bool isV = sym == C_VERTEX, isL = sym == C_LEFT;
-	const uint32_t stop = __ballot_sync(FULL, !(isV || isL));
-	const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
-	if(m < 2) return 0;
-	const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
-	const uint32_t Vm = __ballot_sync(FULL, isV) & pm, Lm = __ballot_sync(FULL, isL) & pm;
-	const uint32_t nV = __popc(Vm), nL = __popc(Lm);
-	uint32_t ok = 1;
-	// Fast path for the prev chain: the edges a strip consumes on its left are usually the queued edges of ONE earlier strip,
-	// created back to back and linked in creation order (prev of id k is k+1).  Every lane checks one link; if all of them
-	// hold the chain is p0, p0+1, ... and nothing is walked.  Any mismatch falls back to the serial walk.
-	const uint32_t p0 = __shfl_sync(FULL, S.cprev, 0);
-	bool consecutive = false;
-	if(nL) {
-		const uint32_t idk = p0 + lane;
-		uint32_t pk = 0xffffffffu, pn;
-		if(lane < nL && idk >= eflush && idk < nfront0 && idk != next0) rg.ldB(idk, pk, pn);
-		consecutive = __all_sync(FULL, lane >= nL || pk == idk + 1);
-		if(consecutive && lane <= nL) chain[lane] = p0 + lane;
-		if(consecutive && lane == 0) chain[nL] = p0 + nL;
-	}
-	if(lane == 0) {
-		uint32_t p = S.cprev;
-		if(nfront0 + nV > io.cap) ok = 0;
-		for(uint32_t k = 0; k < nL && !consecutive; k++) {   // the serial part: walk the prev chain
-			chain[k] = p;
-			if(p == next0) ok = 0;                         // the walk wraps around to the right-hand neighbour (small loop): its links
-			                                               // change inside this window, so take the scalar path
-			uint32_t pp, pn;
-			if(p >= eflush) rg.ldB(p, pp, pn); else { const uint2_t t_ = lead_g_load(io.eb, p); pp = t_.x; pn = t_.y; }
-			(void)pn;
-			p = pp;
+	uint32_t cler = __shfl_sync(FULL, S.cler, 0), start = __shfl_sync(FULL, S.start, 0);
+	const uint32_t end = __shfl_sync(FULL, S.end, 0), eflush = __shfl_sync(FULL, S.eflush, 0);
+	uint32_t nfront = __shfl_sync(FULL, S.nfront, 0), next = __shfl_sync(FULL, S.cnext, 0), prev = __shfl_sync(FULL, S.cprev, 0);
+	uint32_t nlog = __shfl_sync(FULL, S.nlog, 0);
+	const uint32_t below = (1u << lane) - 1u;
+	uint32_t done = 0;
+	for(;;) {
+		const uint32_t lim = min(min(32u, left - done), min(io.nclers - cler, end - start));
+		if(lim < 2) break;
+		uint32_t sym = pre.sym;
+		if(pre.at != cler) sym = cler + lane < io.nclers ? (uint32_t)io.clers[cler + lane] : 0xffu;
+		const bool isV = lane < lim && sym == C_VERTEX, isL = lane < lim && sym == C_LEFT;
+		const uint32_t stop = __ballot_sync(FULL, !(isV || isL));
+		const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+		if(m < 2) { pre.at = cler; pre.sym = sym; break; }
+		pre.at = cler + m;                                 // the usual case: the run goes on right behind this window
+		pre.sym = pre.at + lane < io.nclers ? (uint32_t)io.clers[pre.at + lane] : 0xffu;
+		const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
+		const uint32_t Vm = __ballot_sync(FULL, isV) & pm, Lm = __ballot_sync(FULL, isL) & pm;
+		const uint32_t nV = __popc(Vm), nL = __popc(Lm);
+		if(nfront + nV > io.cap) break;                    // the scalar machine flags it
+		// Fast path for the prev chain: the edges a strip consumes on its left are usually the queued edges of ONE earlier strip,
+		// created back to back and linked in creation order (prev of id k is k+1).  Every lane checks one link; if all of them
+		// hold the chain is prev, prev+1, ... and nothing is walked.  Any mismatch falls back to the serial walk.
+		uint32_t p = prev + __popc(Lm & below), newprev = prev + nL;
+		if(nL) {
+			const uint32_t idk = prev + lane;
+			uint32_t pk = 0xffffffffu, pn;
+			if(lane < nL && idk >= eflush && idk < nfront && idk != next) rg.ldB(idk, pk, pn);
+			if(!__all_sync(FULL, lane >= nL || pk == idk + 1)) {
+				uint32_t ok = 1;
+				if(lane == 0) {
+					uint32_t q = prev;
+					for(uint32_t k = 0; k < nL; k++) {         // the serial part: walk the prev chain
+						chain[k] = q;
+						if(q == next) ok = 0;                  // the walk wraps around to the right-hand neighbour (small loop): its links
+						                                       // change inside this window, so take the scalar path
+						uint32_t pp, pq;
+						if(q >= eflush) rg.ldB(q, pp, pq); else { const uint2_t t_ = lead_g_load(io.eb, q); pp = t_.x; pq = t_.y; }
+						(void)pq;
+						q = pp;
+					}
+					chain[nL] = q;
+				}
+				__syncwarp();
+				ok = __shfl_sync(FULL, ok, 0);
+				if(!ok) break;
+				p = chain[__popc(Lm & below)]; newprev = chain[nL];
+			}
 		}
-		if(!consecutive) chain[nL] = p;
-	}
-	__syncwarp();
-	ok = __shfl_sync(FULL, ok, 0);
-	if(!ok) return 0;
-	if(lane < m) {
-		const uint32_t below = (1u << lane) - 1u;
-		if(isV) {
-			const uint32_t r = __popc(Vm & below), b = nfront0 + r;
-			rg.stB(b, r + 1 < nV ? b + 1 : CLERS_NOLINK, r ? b - 1 : next0);
-			rg.stFl(b, 0);
-			rg.stLog(nlog0 + lane, ((uint32_t)LG_V << 28) | b);
-		} else {
-			const uint32_t p = chain[__popc(Lm & below)];
-			if(p >= eflush) rg.stFl(p, CLERS_DEL); else lead_g_set_flag(io.fl, p, CLERS_DEL);
-			rg.stLog(nlog0 + lane, ((uint32_t)LG_L << 28) | p);
+		if(lane < m) {
+			if(isV) {
+				const uint32_t r = __popc(Vm & below), b = nfront + r;
+				rg.stB(b, r + 1 < nV ? b + 1 : CLERS_NOLINK, r ? b - 1 : next);
+				rg.stFl(b, 0);
+				rg.stLog(nlog + lane, ((uint32_t)LG_V << 28) | b);
+			} else {
+				if(p >= eflush) rg.stFl(p, CLERS_DEL); else lead_g_set_flag(io.fl, p, CLERS_DEL);
+				rg.stLog(nlog + lane, ((uint32_t)LG_L << 28) | p);
+			}
 		}
+		if(nV) {
+			if(lane == 0) { if(next >= eflush) rg.stB_prev(next, nfront); else clers_g_set_prev(io.eb, next, nfront); }
+			nfront += nV; next = nfront - 1;
+		}
+		prev = newprev;
+		nlog += m; start += m; cler += m; done += m;
+		__syncwarp();                                      // this window's ring stores before the next window's loads (and `chain` reuse)
+		if(start >= end) break;
 	}
-	if(lane == 0) {
-		if(nV) { if(next0 >= eflush) rg.stB_prev(next0, nfront0); else clers_g_set_prev(io.eb, next0, nfront0); }
-		S.nfront = nfront0 + nV;
-		S.cprev = chain[nL];
-		if(nV) S.cnext = nfront0 + nV - 1;
+	if(done && lane == 0) {
+		S.nfront = nfront; S.cprev = prev; S.cnext = next;
 		S.lp = S.ln = 1; S.cf = CLERS_NOID;
-		S.nlog = nlog0 + m; S.start = start + m;
-		S.cler = cler + m; S.cwv = 0;                       // the scalar machine re-primes its symbol window when it next runs
-		if(S.start >= S.end) S.have = 0;
+		S.nlog = nlog; S.start = start;
+		S.cler = cler; S.cwv = 0;                           // the scalar machine re-primes its symbol window when it next runs
+		if(start >= end) S.have = 0;
 	}
-	__syncwarp();
-	return m;
+	return done;
 }
 
 // Implicit-FIFO pop, 32 flag bytes per step: most queued edges are dead by the time the scan reaches them (a grid deletes
@@ -537,59 +553,92 @@ __device__ void lead_pop_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 	__syncwarp();
 }
 
+// Drain of the staged faces [f0, f1) and predictions [p0, p1) to global memory (all lanes).
+__device__ __forceinline__ void follow_drain(const ClersIO &io, const SmemRings4 &rg, uint32_t oF, uint32_t oP, uint32_t f0, uint32_t f1, uint32_t p0, uint32_t p1, uint32_t lane) {
+	const uint32_t nw = (f1 - f0)*3u;
+	const uint4 *sf = (const uint4 *)(crt_smem + oF);
+	for(uint32_t k = lane; k < nw; k += 32) {
+		const uint32_t face = f0 + k/3u, comp = k - (k/3u)*3u;
+		const uint32_t v = ((const uint32_t *)(sf + (face & rg.FM)))[comp];
+		const size_t at = (size_t)f0*3u + k;
+		if(io.faces16) io.faces16[at] = (uint16_t)v; else io.faces32[at] = v;
+	}
+	const uint4 *sp = (const uint4 *)(crt_smem + oP);
+	uint4 *dst = (uint4 *)io.pred;
+	for(uint32_t v = p0 + lane; v < p1; v += 32) dst[v] = sp[v & rg.PM];
+}
+
 // Label machine over a run of VERTEX / LEFT log words: "who defined v0 / v1 last" is a bit trick on the ballot masks,
-// label loads of the LEFTs go out in parallel, faces / predictions / labels are staged by 32 lanes at once.
-__device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState &F, uint32_t upto, uint32_t lane) {
+// label loads of the LEFTs go out in parallel.  Like lead_vector, one call runs window after window on warp-uniform
+// state.  Faces and predictions of a window go straight to global memory (one face / one prediction per lane; whatever
+// the scalar machine had staged before is drained first so that the staged range stays a contiguous suffix).
+// Returns the number of log words consumed.
+__device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState &F, uint32_t upto, uint32_t lane, uint32_t oF, uint32_t oP) {
 	const uint32_t FULL = 0xffffffffu;
 	__syncwarp();
-	const uint32_t tail = __shfl_sync(FULL, F.tail, 0);
-	const uint32_t lim = min(32u, upto - tail);
-	const uint32_t w = lane < lim ? rg.ldLog(tail + lane) : 0xffffffffu;
-	const uint32_t t = w >> 28, id = w & 0x0FFFFFFFu;
-	const bool isV = t == LG_V, isL = t == LG_L;
-	uint32_t stop = __ballot_sync(FULL, !(isV || isL));
-	// a LEFT may consume an edge that a VERTEX of this very window creates (the prev chain wrapped around a small loop): its
-	// label does not exist yet, so the window ends in front of it.  Ids grow with creation order: compare with the first V's.
-	const uint32_t vall = __ballot_sync(FULL, isV);
-	const uint32_t firstid = __shfl_sync(FULL, id, vall ? __ffs(vall) - 1 : 0);
-	stop |= __ballot_sync(FULL, isL && vall && id >= firstid && (uint32_t)(__ffs(vall) - 1) < lane);
-	const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
-	if(m < 2) return 0;
-	const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
-	const uint32_t Vm = vall & pm, Lm = __ballot_sync(FULL, isL) & pm;
-	const uint32_t nV = __popc(Vm);
-	const uint32_t vcount0 = __shfl_sync(FULL, F.vcount, 0), nf0 = __shfl_sync(FULL, F.nfaces, 0), aflush = __shfl_sync(FULL, F.aflush, 0);
-	const uint32_t v0i = __shfl_sync(FULL, F.v0, 0), v1i = __shfl_sync(FULL, F.v1, 0), v2i = __shfl_sync(FULL, F.v2, 0);
-	if(vcount0 + nV > io.nvert || nf0 + m > io.nface) return 0;     // let the scalar machine flag the error
-	uint32_t a = 0;
-	if(lane < m && isL) {
-		uint32_t t1, t2;
-		if(id >= aflush) rg.ldA(id, a, t1, t2); else { const uint4_t g_ = follow_g_load(io.ea, id); a = g_.x; }
-	}
+	uint32_t tail = __shfl_sync(FULL, F.tail, 0);
+	if(upto - tail < 2) return 0;
+	uint32_t vcount = __shfl_sync(FULL, F.vcount, 0), nf = __shfl_sync(FULL, F.nfaces, 0), amax = __shfl_sync(FULL, F.amax, 0);
+	const uint32_t aflush = __shfl_sync(FULL, F.aflush, 0);
+	uint32_t v0 = __shfl_sync(FULL, F.v0, 0), v1 = __shfl_sync(FULL, F.v1, 0), v2 = __shfl_sync(FULL, F.v2, 0);
 	const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
-	const uint32_t x = vcount0 + __popc(Vm & lt);
-	const uint32_t lLE = Lm & le, lLT = Lm & lt, vLE = Vm & le, vLT = Vm & lt;
-	const uint32_t a_le = __shfl_sync(FULL, a, lLE ? 31 - __clz(lLE) : 0), a_lt = __shfl_sync(FULL, a, lLT ? 31 - __clz(lLT) : 0);
-	const uint32_t x_le = __shfl_sync(FULL, x, vLE ? 31 - __clz(vLE) : 0), x_lt = __shfl_sync(FULL, x, vLT ? 31 - __clz(vLT) : 0);
-	const uint32_t v0_after = lLE ? a_le : v0i, v0_before = lLT ? a_lt : v0i;
-	const uint32_t v1_after = vLE ? x_le : v1i, v1_before = vLT ? x_lt : v1i;
-	const uint32_t pv1b = __shfl_up_sync(FULL, v1_before, 1), pv0b = __shfl_up_sync(FULL, v0_before, 1);
-	const uint32_t v2_before = lane == 0 ? v2i : (((Vm >> (lane - 1)) & 1u) ? pv1b : pv0b);
-	if(lane < m) {
-		rg.stF(nf0 + lane, v1_before, v0_before, isV ? x : a);
-		if(isV) { rg.stP(x, v1_before, v0_before, v2_before); rg.stA(id, x, v1_before, v0_before); }
+	uint32_t done = 0;
+	for(;;) {
+		const uint32_t lim = min(32u, upto - tail);
+		if(lim < 2) break;
+		const uint32_t w = lane < lim ? rg.ldLog(tail + lane) : 0xffffffffu;
+		const uint32_t t = w >> 28, id = w & 0x0FFFFFFFu;
+		const bool isV = t == LG_V, isL = t == LG_L;
+		uint32_t stop = __ballot_sync(FULL, !(isV || isL));
+		// a LEFT may consume an edge that a VERTEX of this very window creates (the prev chain wrapped around a small loop): its
+		// label does not exist yet, so the window ends in front of it.  Ids grow with creation order: compare with the first V's.
+		const uint32_t vall = __ballot_sync(FULL, isV);
+		const uint32_t firstid = __shfl_sync(FULL, id, vall ? __ffs(vall) - 1 : 0);
+		stop |= __ballot_sync(FULL, isL && vall && id >= firstid && (uint32_t)(__ffs(vall) - 1) < lane);
+		const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+		if(m < 2) break;
+		const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
+		const uint32_t Vm = vall & pm, Lm = __ballot_sync(FULL, isL) & pm;
+		const uint32_t nV = __popc(Vm);
+		if(vcount + nV > io.nvert || nf + m > io.nface) break;          // let the scalar machine flag the error
+		if(!done) {                                                     // first window of this call: flush what the scalar machine staged
+			const uint32_t f0 = __shfl_sync(FULL, F.fflush, 0), p0 = __shfl_sync(FULL, F.pflush, 0);
+			if(f0 != nf || p0 != vcount) follow_drain(io, rg, oF, oP, f0, nf, p0, vcount, lane);
+		}
+		uint32_t a = 0;
+		if(lane < m && isL) {
+			uint32_t t1, t2;
+			if(id >= aflush) rg.ldA(id, a, t1, t2); else { const uint4_t g_ = follow_g_load(io.ea, id); a = g_.x; }
+		}
+		const uint32_t x = vcount + __popc(Vm & lt);
+		const uint32_t lLE = Lm & le, lLT = Lm & lt, vLE = Vm & le, vLT = Vm & lt;
+		const uint32_t a_le = __shfl_sync(FULL, a, lLE ? 31 - __clz(lLE) : 0), a_lt = __shfl_sync(FULL, a, lLT ? 31 - __clz(lLT) : 0);
+		const uint32_t x_le = __shfl_sync(FULL, x, vLE ? 31 - __clz(vLE) : 0), x_lt = __shfl_sync(FULL, x, vLT ? 31 - __clz(vLT) : 0);
+		const uint32_t v0_after = lLE ? a_le : v0, v0_before = lLT ? a_lt : v0;
+		const uint32_t v1_after = vLE ? x_le : v1, v1_before = vLT ? x_lt : v1;
+		const uint32_t pv1b = __shfl_up_sync(FULL, v1_before, 1), pv0b = __shfl_up_sync(FULL, v0_before, 1);
+		const uint32_t v2_before = lane == 0 ? v2 : (((Vm >> (lane - 1)) & 1u) ? pv1b : pv0b);
+		if(lane < m) {
+			const size_t at = (size_t)(nf + lane)*3u;
+			const uint32_t third = isV ? x : a;
+			if(io.faces16) { io.faces16[at] = (uint16_t)v1_before; io.faces16[at + 1] = (uint16_t)v0_before; io.faces16[at + 2] = (uint16_t)third; }
+			else { io.faces32[at] = v1_before; io.faces32[at + 1] = v0_before; io.faces32[at + 2] = third; }
+			if(isV) { ((uint4 *)io.pred)[x] = make_uint4(v1_before, v0_before, v2_before, 0u); rg.stA(id, x, v1_before, v0_before); }
+		}
+		const uint32_t last = m - 1;
+		const uint32_t v0e = __shfl_sync(FULL, v0_after, last), v1e = __shfl_sync(FULL, v1_after, last);
+		const uint32_t v2e = __shfl_sync(FULL, isV ? v1_before : v0_before, last);
+		if(nV) amax = __shfl_sync(FULL, id, 31 - __clz(Vm)) + 1u;
+		v0 = v0e; v1 = v1e; v2 = v2e;
+		vcount += nV; nf += m; tail += m; done += m;
+		__syncwarp();                                                   // this window's labels before the next window's loads
 	}
-	const uint32_t last = m - 1;
-	const uint32_t v0e = __shfl_sync(FULL, v0_after, last), v1e = __shfl_sync(FULL, v1_after, last);
-	const uint32_t v2e = __shfl_sync(FULL, isV ? v1_before : v0_before, last);
-	const uint32_t topid = __shfl_sync(FULL, id, Vm ? 31 - __clz(Vm) : 0);
-	if(lane == 0) {
-		F.v0 = v0e; F.v1 = v1e; F.v2 = v2e;
-		F.vcount = vcount0 + nV; F.nfaces = nf0 + m; F.tail = tail + m;
-		if(nV) F.amax = topid + 1;
+	if(done && lane == 0) {
+		F.v0 = v0; F.v1 = v1; F.v2 = v2;
+		F.vcount = vcount; F.nfaces = nf; F.tail = tail; F.amax = amax;
+		F.fflush = nf; F.pflush = vcount;
 	}
-	__syncwarp();
-	return m;
+	return done;
 }
 
 constexpr int LF_BUDGET = 160;          // symbols per leader chunk / log words per follower batch
@@ -637,6 +686,7 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 			// ------------------------------------------------ leader ------------------------------------------------
 			LeadState S;
 			lead_init(S, io);
+			LeadPre pre{0xffu, 0xffffffffu};
 			int rc = 0;
 			for(;;) {
 				if(lane == 0) {      // wait for log space (the follower is at most one ring behind)
@@ -650,11 +700,8 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 				// one chunk: scalar machine, interleaved with warp-wide windows over VERTEX/LEFT runs
 				uint32_t left = LF_BUDGET;
 				bool tried = false;                                // the last window attempt bailed: one symbol goes the scalar way
+				if(vecmode && rc == 0) left -= lead_vector(io, rg, S, left, chain, lane, pre);   // a chunk usually starts in the middle of a run
 				while(rc == 0 && left > 0) {
-					if(vecmode && left >= 2 && !tried) {
-						const uint32_t m = lead_vector(io, rg, S, left, chain, lane);
-						if(m) { left = left > m ? left - m : 0; continue; }
-					}
 					uint32_t c0 = 0;
 					if(lane == 0) { c0 = S.cler; rc = clers_lead(io, rg, S, tried ? 1 : (int)left, vecmode && !tried); c0 = S.cler - c0; }
 					rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -663,8 +710,8 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 					tried = false;
 					if(rc == 3) {                                  // the scalar machine saw a VERTEX/LEFT run coming
 						rc = 0;
-						const uint32_t m = left >= 2 ? lead_vector(io, rg, S, left, chain, lane) : 0;
-						if(m) left = left > m ? left - m : 0; else tried = true;
+						const uint32_t m = left >= 2 ? lead_vector(io, rg, S, left, chain, lane, pre) : 0;
+						if(m) left -= m; else tried = true;
 					} else if(rc == 4) {                           // it needs the next queued edge
 						rc = 0;
 						lead_pop_vector(io, rg, S, lane);
@@ -709,12 +756,12 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 					const uint32_t t0 = __shfl_sync(0xffffffffu, F.tail, 0);
 					const uint32_t upto = min(head, t0 + (uint32_t)LF_BUDGET);
 					bool tried = false;
+					if(vecmode && rc == 0) follow_vector(io, rg, F, upto, lane, oF, oP);   // a batch usually starts in the middle of a run
 					while(rc == 0 && __shfl_sync(0xffffffffu, F.tail, 0) < upto) {
-						if(vecmode && !tried && follow_vector(io, rg, F, upto, lane)) continue;
 						if(lane == 0) rc = clers_follow(io, rg, F, tried ? F.tail + 1 : upto, LF_STAGE, splitbits, vecmode && !tried);
 						rc = __shfl_sync(0xffffffffu, rc, 0);
 						tried = false;
-						if(rc == 3) { rc = 0; if(follow_vector(io, rg, F, upto, lane) == 0) tried = true; }
+						if(rc == 3) { rc = 0; if(follow_vector(io, rg, F, upto, lane, oF, oP) == 0) tried = true; }
 					}
 				}
 				// ---- drains (all lanes) ----
@@ -722,19 +769,7 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 				const uint32_t p0 = __shfl_sync(0xffffffffu, F.pflush, 0), p1 = __shfl_sync(0xffffffffu, F.vcount, 0);
 				const uint32_t a0 = __shfl_sync(0xffffffffu, F.aflush, 0), am = __shfl_sync(0xffffffffu, F.amax, 0);
 				const uint32_t tl = __shfl_sync(0xffffffffu, F.tail, 0);
-				{
-					const uint32_t nw = (f1 - f0)*3u;
-					const uint4 *sf = (const uint4 *)(crt_smem + oF);
-					for(uint32_t k = lane; k < nw; k += 32) {
-						const uint32_t face = f0 + k/3u, comp = k - (k/3u)*3u;
-						const uint32_t v = ((const uint32_t *)(sf + (face & rg.FM)))[comp];
-						const size_t at = (size_t)f0*3u + k;
-						if(io.faces16) io.faces16[at] = (uint16_t)v; else io.faces32[at] = v;
-					}
-					const uint4 *sp = (const uint4 *)(crt_smem + oP);
-					uint4 *dst = (uint4 *)io.pred;
-					for(uint32_t v = p0 + lane; v < p1; v += 32) dst[v] = sp[v & rg.PM];
-				}
+				if(f0 != f1 || p0 != p1) follow_drain(io, rg, oF, oP, f0, f1, p0, p1, lane);
 				uint32_t a1 = am > WA ? am - WA : 0u;
 				if(rc == 2) a1 = 0;
 				if(a1 > a0) for(uint32_t id = a0 + lane; id < a1; id += 32) { const uint4 a = ((const uint4 *)(crt_smem + oA))[id & rg.AM]; io.ea[id] = EdgeA{a.x, a.y, a.z, 0}; }
@@ -773,7 +808,7 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 //          in-place reference loop, vertex_attribute.h:165-176).
 // =========================================================================================================
 template <typename T, int NC>
-__device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint32_t nvert, bool par, int lane) {
+__device__ __forceinline__ void delta_mesh_rounds(T *v, const uint32_t stride, const uint4 *pred, uint32_t nvert, bool par, int lane) {
 	// Two-deep software pipeline over rounds of 32 vertices:
 	//   * prediction + residuals are fetched TWO rounds ahead (they are streams nobody writes before their round);
 	//   * the operand gather of round r+1 is issued BEFORE round r is resolved, for every operand that is already final
@@ -786,8 +821,8 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 	uint32_t xA[NC], xB[NC], xprev[NC];
 #pragma unroll
 	for(int k = 0; k < NC; k++) {
-		xA[k] = (uint32_t)lane < nvert ? (uint32_t)v[(size_t)lane*NC + k] : 0u;
-		xB[k] = 32u + lane < nvert ? (uint32_t)v[(size_t)(32u + lane)*NC + k] : 0u;
+		xA[k] = (uint32_t)lane < nvert ? (uint32_t)v[(size_t)lane*stride + k] : 0u;
+		xB[k] = 32u + lane < nvert ? (uint32_t)v[(size_t)(32u + lane)*stride + k] : 0u;
 		xprev[k] = 0;
 	}
 	// gathered operands of the current round + which of them wait for the previous round's registers
@@ -799,9 +834,9 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 		const bool act = i < nvert && i > 0;
 #pragma unroll
 		for(int k = 0; k < NC; k++) {
-			fa[k] = (act && pA.x >= 32u && pA.x < nvert) ? (uint32_t)v[(size_t)pA.x*NC + k] : 0u;
-			fb[k] = (act && par && pA.y >= 32u && pA.y < nvert) ? (uint32_t)v[(size_t)pA.y*NC + k] : 0u;
-			fc[k] = (act && par && pA.z >= 32u && pA.z < nvert) ? (uint32_t)v[(size_t)pA.z*NC + k] : 0u;
+			fa[k] = (act && pA.x >= 32u && pA.x < nvert) ? (uint32_t)v[(size_t)pA.x*stride + k] : 0u;
+			fb[k] = (act && par && pA.y >= 32u && pA.y < nvert) ? (uint32_t)v[(size_t)pA.y*stride + k] : 0u;
+			fc[k] = (act && par && pA.z >= 32u && pA.z < nvert) ? (uint32_t)v[(size_t)pA.z*stride + k] : 0u;
 		}
 	}
 	for(uint32_t base = 0; base < nvert; base += 32) {
@@ -831,7 +866,7 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 				const bool in_next = use && X - nb < 32u;                // inside its own round
 				if(in_this) pend_n |= bit;
 #pragma unroll
-				for(int k = 0; k < NC; k++) g[k] = (use && !in_this && !in_next && X < nvert) ? (uint32_t)v[(size_t)X*NC + k] : 0u;
+				for(int k = 0; k < NC; k++) g[k] = (use && !in_this && !in_next && X < nvert) ? (uint32_t)v[(size_t)X*stride + k] : 0u;
 			};
 			far(na, nact, 1u, ga); far(nbb, nact && par, 2u, gb); far(nc, nact && par, 4u, gc);
 		}
@@ -839,12 +874,12 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 		const uint4 pC = ldp(i2);
 		uint32_t xC[NC];
 #pragma unroll
-		for(int k = 0; k < NC; k++) xC[k] = i2 < nvert ? (uint32_t)v[(size_t)i2*NC + k] : 0u;
+		for(int k = 0; k < NC; k++) xC[k] = i2 < nvert ? (uint32_t)v[(size_t)i2*stride + k] : 0u;
 		{
 			const uint32_t farv = i + 32u*10u;                          // pull the streams into L2 well ahead
 			if(farv < nvert) {
 				asm volatile("prefetch.global.L2 [%0];" :: "l"(pred + farv));
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(v + (size_t)farv*NC));
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(v + (size_t)farv*stride));
 			}
 		}
 		// ---- resolve this round ----
@@ -902,7 +937,7 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint4 *pred, uint3
 		}
 		if(act) {
 #pragma unroll
-			for(int k = 0; k < NC; k++) v[(size_t)i*NC + k] = (T)x[k];
+			for(int k = 0; k < NC; k++) v[(size_t)i*stride + k] = (T)x[k];
 		}
 		__syncwarp();
 		// ---- rotate the pipeline ----
@@ -917,29 +952,18 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 	if(w >= nwork) return;
 	const int lane = threadIdx.x;
 	const MeshDesc *M = B.mesh + work[w].x;
-	const AttrDesc *A = &M->attr[work[w].y];
+	const AttrDesc *A = &M->attr[work[w].y & 0xffu];
 	if(B.status[work[w].x]) return;
 	const uint32_t nvert = M->nvert;
 	const uint4 *pred = (const uint4 *)M->pred_ptr;
 	const int nc = A->ncomp;
 	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;    // normals: d += d[a] only (normal_attribute.cpp:193-201)
-	if(A->codec == CODEC_COLOR) {
-		uint8_t *v = (uint8_t *)A->work_ptr;
-		switch(nc) {
-		case 1: delta_mesh_rounds<uint8_t, 1>(v, pred, nvert, par, lane); break;
-		case 2: delta_mesh_rounds<uint8_t, 2>(v, pred, nvert, par, lane); break;
-		case 3: delta_mesh_rounds<uint8_t, 3>(v, pred, nvert, par, lane); break;
-		default: delta_mesh_rounds<uint8_t, 4>(v, pred, nvert, par, lane); break;
-		}
-	} else {
-		uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
-		switch(nc) {
-		case 1: delta_mesh_rounds<uint32_t, 1>(v, pred, nvert, par, lane); break;
-		case 2: delta_mesh_rounds<uint32_t, 2>(v, pred, nvert, par, lane); break;
-		case 3: delta_mesh_rounds<uint32_t, 3>(v, pred, nvert, par, lane); break;
-		default: delta_mesh_rounds<uint32_t, 4>(v, pred, nvert, par, lane); break;
-		}
-	}
+	// One warp per COMPONENT: the recurrence is component-wise, so the nc components of an attribute are independent chains;
+	// a warp walks one of them (interleaved values, stride nc) and the per-round instruction count — the bound of this
+	// latency-limited kernel — drops with it.  Each warp reads the prediction stream itself (L2-resident after the first).
+	const uint32_t comp = work[w].y >> 8;
+	if(A->codec == CODEC_COLOR) delta_mesh_rounds<uint8_t, 1>((uint8_t *)A->work_ptr + comp, (uint32_t)nc, pred, nvert, par, lane);
+	else delta_mesh_rounds<uint32_t, 1>((uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr) + comp, (uint32_t)nc, pred, nvert, par, lane);
 }
 
 // =========================================================================================================
