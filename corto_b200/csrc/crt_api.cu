@@ -80,9 +80,9 @@ struct crt_batch {
 	bool profiling = false;
 	std::vector<Stage> stages;
 	std::vector<int> h_status;
-	// intra-batch overlap: the attribute unpack runs beside the CLERS automaton, the adjacency build beside the delta inverse
+	// optional intra-batch overlap (CORTO_OVERLAP=1): the attribute unpack runs beside the CLERS automaton on a side stream
 	cudaStream_t side = nullptr;
-	cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+	cudaEvent_t ev_fork[1] = {nullptr}, ev_join[1] = {nullptr};
 	int overlap = -1;                  // -1: read CORTO_OVERLAP on first use
 };
 
@@ -111,7 +111,7 @@ static void batch_free_device(crt_batch *b) {
 	b->d_blobs = b->d_tables = b->d_scratch = b->d_zero = nullptr;
 	for(auto &s: b->stages) cudaEventDestroy(s.ev);
 	b->stages.clear();
-	for(int k = 0; k < 2; k++) {
+	for(int k = 0; k < 1; k++) {
 		if(b->ev_fork[k]) cudaEventDestroy(b->ev_fork[k]);
 		if(b->ev_join[k]) cudaEventDestroy(b->ev_join[k]);
 		b->ev_fork[k] = b->ev_join[k] = nullptr;
@@ -285,8 +285,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			}
 			// delta inverse
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
-				for(int c = 0; c < A.ncomp; c++)                                      // one warp per component (k_delta_mesh)
-					b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a | ((unsigned)c << 8)));   // meshes only: clouds went through the fused kernel
+				b->w_delta.push_back(make_uint2((unsigned)i, (unsigned)a | 0xff00u | ((unsigned)A.ncomp << 16)));   // all components; meshes only: clouds went through the fused kernel
 			}
 			// dequantise (normals: only DIFF goes through k_dequant; ESTIMATED/BORDER are finished by k_normal_estimate)
 			if(pa.codec != CODEC_NORMAL || normal_diff) {
@@ -306,7 +305,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			csr_off[i] = zero_csr_bytes;
 			zero_csr_bytes += align_up(((uint64_t)pm.nvert*3 + 2)*4, 16);      // cnt | bnd | cidx[+1] | novf
 			adj_off[i] = adj_bytes;
-			adj_bytes += align_up((uint64_t)pm.nvert*32 + (uint64_t)pm.nface*24, 16);   // 8 slots per vertex + overflow pairs
+			adj_bytes += align_up((uint64_t)pm.nface*16 + (uint64_t)pm.nvert*32 + (uint64_t)pm.nface*24, 16);   // face normals + 8 slots per vertex + overflow pairs
 			uint32_t nf = (pm.nface + SCAN_TILE - 1)/SCAN_TILE, nv = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE, ns = (pm.nvert + 1 + SCAN_TILE - 1)/SCAN_TILE;
 			for(uint32_t t = 0; t < nf; t++) b->t_faces.push_back(Tile{(uint32_t)i, 0, t, 0});
 			for(uint32_t t = 0; t < nv; t++) b->t_verts.push_back(Tile{(uint32_t)i, 0, t, 0});
@@ -428,6 +427,16 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->o_t_faces = put(img, b->t_faces);
 	b->o_t_verts = put(img, b->t_verts);
 	b->o_t_vscan = put(img, b->t_vscan);
+	// Delta work items: one warp per (mesh, attribute) walks all components together (they share the prediction loads and
+	// interleave in the pipeline).  When that leaves most SMs without a warp (few, large meshes) the components — independent
+	// chains — get a warp each instead: measured 94 -> 80 ms on 64 x 1.7 M-vertex meshes, no gain (c2) or a loss (c4) on big batches.
+	const char *force = getenv("CORTO_DELTA_SPLIT");                // 0 / 1 overrides the heuristic (tests, A/B runs)
+	if(force ? force[0] == '1' : b->w_delta.size() < 2u*(size_t)b->sms) {
+		std::vector<uint2> split;
+		for(const uint2 &w: b->w_delta)
+			for(unsigned c = 0; c < (w.y >> 16); c++) split.push_back(make_uint2(w.x, (w.y & 0xffu) | (c << 8)));
+		b->w_delta.swap(split);
+	}
 	b->o_w_delta = put(img, b->w_delta);
 	b->o_order = put(img, b->clers_order);
 	b->o_t_cfused = put(img, b->t_cfused);
@@ -525,19 +534,17 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
 	st += b->t_tun.size();
 	if((rc = mark(b, "tun_decode", k, s))) return rc;
-	// Stage order inside one batch.  Default: every stage on the caller's stream.  CORTO_OVERLAP (bit 0: attribute unpack beside
-	// the CLERS automaton, bit 1: adjacency build beside the delta inverse, both on a side stream) is an experiment switch: the
-	// two latency-bound kernels leave most SMs idle, but on B200 the company costs them more than it saves (measured on
-	// configs[1]: 13.1 ms with both overlaps vs 11.7 ms serial — the automaton's two warps per mesh lose issue slots and L1 to
-	// the wide kernel), so it is off unless asked for.  Stage timers (profiling) always run serial.
-	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 3 : 0; }
+	// Stage order inside one batch.  Default: every stage on the caller's stream.  CORTO_OVERLAP=1 (attribute unpack beside the
+	// CLERS automaton on a side stream) is an experiment switch: the automaton leaves most SMs idle, but on B200 the company
+	// costs it more than it saves (measured on configs[1]: 13.1 ms overlapped vs 11.7 ms serial — the automaton's two warps per
+	// mesh lose issue slots and L1 to the wide kernel), so it is off unless asked for.  Stage timers (profiling) always run serial.
+	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 1 : 0; }
 	const bool ovl = (b->overlap & 1) && !b->profiling && !b->clers_order.empty() && !b->t_bits.empty();
-	const bool want2 = (b->overlap & 2) && !b->profiling && !b->t_faces.empty() && !b->w_delta.empty();
 	cudaStream_t s2 = s;
-	if(ovl || want2) {
+	if(ovl) {
 		if(!b->side) {
 			CU(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
-			for(int k2 = 0; k2 < 2; k2++) {
+			for(int k2 = 0; k2 < 1; k2++) {
 				CU(cudaEventCreateWithFlags(&b->ev_fork[k2], cudaEventDisableTiming));
 				CU(cudaEventCreateWithFlags(&b->ev_join[k2], cudaEventDisableTiming));
 			}
@@ -562,20 +569,12 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 		RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
 	}
 	if((rc = mark(b, "clers", k, s))) return rc;
-	const bool ovl2 = want2;
-	if(ovl2) CU(cudaEventRecord(b->ev_fork[1], s));
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
 	if((rc = mark(b, "delta", k, s))) return rc;
-	if(!b->t_faces.empty()) {
-		cudaStream_t sa = ovl2 ? b->side : s;
-		if(ovl2) CU(cudaStreamWaitEvent(sa, b->ev_fork[1], 0));
-		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), sa), true);
-		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, sa), b->any_border);
+	if(!b->t_faces.empty()) {                      // (the adjacency build reads the delta-decoded positions: it cannot move in front of the delta inverse)
+		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
+		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
 		st += b->t_vscan.size();
-		if(ovl2) {
-			CU(cudaEventRecord(b->ev_join[1], sa));
-			CU(cudaStreamWaitEvent(s, b->ev_join[1], 0));
-		}
 		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
 	}
 	if((rc = mark(b, "normals", k, s))) return rc;

@@ -77,7 +77,7 @@ struct MeshDesc {
 	int32_t position_attr;    // index of the "position" attribute, -1 if none
 	int32_t normal_attr;      // index of a bound ESTIMATED/BORDER normal attribute needing postDelta, else -1
 	uint64_t csr_ptr;         // device scratch (zeroed per decode) for normal estimation: u32 cnt[nvert] | bnd[nvert] | cidx[nvert+1] | novf
-	uint64_t adj_ptr;         // device scratch: u32 adj8[8*nvert] (incident faces, 8 slots per vertex) | uint2 ovf[3*nface] (overflow pairs)
+	uint64_t adj_ptr;         // device scratch: float4 fnormal[nface] (unnormalised face normals) | u32 adj8[8*nvert] (incident faces, 8 slots per vertex) | uint2 ovf[3*nface] (overflow pairs)
 	AttrDesc attr[MAX_ATTR];
 };
 

@@ -493,16 +493,12 @@ __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 				p = chain[__popc(Lm & below)]; newprev = chain[nL];
 			}
 		}
-		if(lane < m) {
-			if(isV) {
-				const uint32_t r = __popc(Vm & below), b = nfront + r;
-				rg.stB(b, r + 1 < nV ? b + 1 : CLERS_NOLINK, r ? b - 1 : next);
-				rg.stFl(b, 0);
-				rg.stLog(nlog + lane, ((uint32_t)LG_V << 28) | b);
-			} else {
-				if(p >= eflush) rg.stFl(p, CLERS_DEL); else lead_g_set_flag(io.fl, p, CLERS_DEL);
-				rg.stLog(nlog + lane, ((uint32_t)LG_L << 28) | p);
-			}
+		if(lane < m) {                                     // one flag byte and one log word per lane, whatever the symbol
+			const uint32_t r = __popc(Vm & below), b = nfront + r;
+			const uint32_t id = isV ? b : p;
+			if(isV) rg.stB(b, r + 1 < nV ? b + 1 : CLERS_NOLINK, r ? b - 1 : next);
+			if(id >= eflush) rg.stFl(id, isV ? 0u : CLERS_DEL); else lead_g_set_flag(io.fl, id, CLERS_DEL);
+			rg.stLog(nlog + lane, ((isV ? (uint32_t)LG_V : (uint32_t)LG_L) << 28) | id);
 		}
 		if(nV) {
 			if(lane == 0) { if(next >= eflush) rg.stB_prev(next, nfront); else clers_g_set_prev(io.eb, next, nfront); }
@@ -581,7 +577,7 @@ __device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState
 	uint32_t vcount = __shfl_sync(FULL, F.vcount, 0), nf = __shfl_sync(FULL, F.nfaces, 0), amax = __shfl_sync(FULL, F.amax, 0);
 	const uint32_t aflush = __shfl_sync(FULL, F.aflush, 0);
 	uint32_t v0 = __shfl_sync(FULL, F.v0, 0), v1 = __shfl_sync(FULL, F.v1, 0), v2 = __shfl_sync(FULL, F.v2, 0);
-	const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
+	const uint32_t lt = (1u << lane) - 1u;
 	uint32_t done = 0;
 	for(;;) {
 		const uint32_t lim = min(32u, upto - tail);
@@ -610,14 +606,14 @@ __device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState
 			uint32_t t1, t2;
 			if(id >= aflush) rg.ldA(id, a, t1, t2); else { const uint4_t g_ = follow_g_load(io.ea, id); a = g_.x; }
 		}
-		const uint32_t x = vcount + __popc(Vm & lt);
-		const uint32_t lLE = Lm & le, lLT = Lm & lt, vLE = Vm & le, vLT = Vm & lt;
-		const uint32_t a_le = __shfl_sync(FULL, a, lLE ? 31 - __clz(lLE) : 0), a_lt = __shfl_sync(FULL, a, lLT ? 31 - __clz(lLT) : 0);
-		const uint32_t x_le = __shfl_sync(FULL, x, vLE ? 31 - __clz(vLE) : 0), x_lt = __shfl_sync(FULL, x, vLT ? 31 - __clz(vLT) : 0);
-		const uint32_t v0_after = lLE ? a_le : v0, v0_before = lLT ? a_lt : v0;
-		const uint32_t v1_after = vLE ? x_le : v1, v1_before = vLT ? x_lt : v1;
-		const uint32_t pv1b = __shfl_up_sync(FULL, v1_before, 1), pv0b = __shfl_up_sync(FULL, v0_before, 1);
-		const uint32_t v2_before = lane == 0 ? v2 : (((Vm >> (lane - 1)) & 1u) ? pv1b : pv0b);
+		// who defined v0 / v1 last before this lane: v1 is a count (vertex ids are consecutive), v0 needs the label of the last LEFT
+		const uint32_t lLT = Lm & lt, vLT = Vm & lt, vLT1 = Vm & (lt >> 1);
+		const uint32_t a_lt = __shfl_sync(FULL, a, lLT ? 31 - __clz(lLT) : 0);
+		const uint32_t v0_before = lLT ? a_lt : v0;
+		const uint32_t x = vcount + __popc(vLT);
+		const uint32_t v1_before = vLT ? x - 1u : v1, v1_before_p = vLT1 ? vcount + __popc(vLT1) - 1u : v1;   // own / lane-1's
+		const uint32_t pv0b = __shfl_up_sync(FULL, v0_before, 1);
+		const uint32_t v2_before = lane == 0 ? v2 : (((Vm >> (lane - 1)) & 1u) ? v1_before_p : pv0b);
 		if(lane < m) {
 			const size_t at = (size_t)(nf + lane)*3u;
 			const uint32_t third = isV ? x : a;
@@ -625,11 +621,10 @@ __device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState
 			else { io.faces32[at] = v1_before; io.faces32[at + 1] = v0_before; io.faces32[at + 2] = third; }
 			if(isV) { ((uint4 *)io.pred)[x] = make_uint4(v1_before, v0_before, v2_before, 0u); rg.stA(id, x, v1_before, v0_before); }
 		}
-		const uint32_t last = m - 1;
-		const uint32_t v0e = __shfl_sync(FULL, v0_after, last), v1e = __shfl_sync(FULL, v1_after, last);
-		const uint32_t v2e = __shfl_sync(FULL, isV ? v1_before : v0_before, last);
-		if(nV) amax = __shfl_sync(FULL, id, 31 - __clz(Vm)) + 1u;
-		v0 = v0e; v1 = v1e; v2 = v2e;
+		const uint32_t v0e = Lm ? __shfl_sync(FULL, a, 31 - __clz(Lm)) : v0;
+		const uint32_t v2e = __shfl_sync(FULL, isV ? v1_before : v0_before, m - 1);
+		if(nV) { amax = __shfl_sync(FULL, id, 31 - __clz(Vm)) + 1u; v1 = vcount + nV - 1u; }
+		v0 = v0e; v2 = v2e;
 		vcount += nV; nf += m; tail += m; done += m;
 		__syncwarp();                                                   // this window's labels before the next window's loads
 	}
@@ -958,12 +953,31 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 	const uint4 *pred = (const uint4 *)M->pred_ptr;
 	const int nc = A->ncomp;
 	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;    // normals: d += d[a] only (normal_attribute.cpp:193-201)
-	// One warp per COMPONENT: the recurrence is component-wise, so the nc components of an attribute are independent chains;
-	// a warp walks one of them (interleaved values, stride nc) and the per-round instruction count — the bound of this
-	// latency-limited kernel — drops with it.  Each warp reads the prediction stream itself (L2-resident after the first).
-	const uint32_t comp = work[w].y >> 8;
-	if(A->codec == CODEC_COLOR) delta_mesh_rounds<uint8_t, 1>((uint8_t *)A->work_ptr + comp, (uint32_t)nc, pred, nvert, par, lane);
-	else delta_mesh_rounds<uint32_t, 1>((uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr) + comp, (uint32_t)nc, pred, nvert, par, lane);
+	const uint32_t comp = (work[w].y >> 8) & 0xffu;
+	if(comp != 0xffu) {
+		// One warp per COMPONENT (the host splits when the batch has few chains): the recurrence is component-wise, so the nc
+		// components of an attribute are independent chains; a warp walks one of them (interleaved values, stride nc).
+		if(A->codec == CODEC_COLOR) delta_mesh_rounds<uint8_t, 1>((uint8_t *)A->work_ptr + comp, (uint32_t)nc, pred, nvert, par, lane);
+		else delta_mesh_rounds<uint32_t, 1>((uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr) + comp, (uint32_t)nc, pred, nvert, par, lane);
+		return;
+	}
+	if(A->codec == CODEC_COLOR) {
+		uint8_t *v = (uint8_t *)A->work_ptr;
+		switch(nc) {
+		case 1: delta_mesh_rounds<uint8_t, 1>(v, 1u, pred, nvert, par, lane); break;
+		case 2: delta_mesh_rounds<uint8_t, 2>(v, 2u, pred, nvert, par, lane); break;
+		case 3: delta_mesh_rounds<uint8_t, 3>(v, 3u, pred, nvert, par, lane); break;
+		default: delta_mesh_rounds<uint8_t, 4>(v, 4u, pred, nvert, par, lane); break;
+		}
+	} else {
+		uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
+		switch(nc) {
+		case 1: delta_mesh_rounds<uint32_t, 1>(v, 1u, pred, nvert, par, lane); break;
+		case 2: delta_mesh_rounds<uint32_t, 2>(v, 2u, pred, nvert, par, lane); break;
+		case 3: delta_mesh_rounds<uint32_t, 3>(v, 3u, pred, nvert, par, lane); break;
+		default: delta_mesh_rounds<uint32_t, 4>(v, 4u, pred, nvert, par, lane); break;
+		}
+	}
 }
 
 // =========================================================================================================
@@ -974,7 +988,7 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 //     corner (one pass over the faces), the rare vertex of higher valence spills (vertex, face) pairs to an overflow list.
 //     zeroed scratch per mesh (u32): cnt[nvert] | bnd[nvert] | cidx[nvert+1] | novf;   plain scratch: adj8[8*nvert] | ovf[3*nface] (uint2)
 // =========================================================================================================
-struct AdjView { uint32_t *cnt, *bnd, *cidx, *novf, *adj8; uint2 *ovf; };
+struct AdjView { uint32_t *cnt, *bnd, *cidx, *novf, *adj8; uint2 *ovf; float4 *fn; };
 __device__ __forceinline__ AdjView adj_view(const MeshDesc *M) {
 	AdjView c;
 	uint32_t *p = (uint32_t *)M->csr_ptr;
@@ -982,7 +996,8 @@ __device__ __forceinline__ AdjView adj_view(const MeshDesc *M) {
 	c.bnd = p; p += M->nvert;
 	c.cidx = p; p += M->nvert + 1;
 	c.novf = p;
-	c.adj8 = (uint32_t *)M->adj_ptr;
+	c.fn = (float4 *)M->adj_ptr;
+	c.adj8 = (uint32_t *)(c.fn + M->nface);
 	c.ovf = (uint2 *)(c.adj8 + (size_t)M->nvert*8);
 	return c;
 }
@@ -991,24 +1006,53 @@ __device__ __forceinline__ void load_face(const MeshDesc *M, uint32_t f, uint32_
 	else { const uint32_t *x = (const uint32_t *)M->face_ptr + (size_t)f*3; a = x[0]; b = x[1]; c = x[2]; }
 }
 
-// tiles: a = mesh, tile = block of SCAN_TILE faces
+// tiles: a = mesh, tile = block of SCAN_TILE faces.  One thread per face:
+//   * its unnormalised normal (the cross product estimateNormals adds to each of its three vertices, normal_attribute.cpp:44-55)
+//     is computed ONCE here from the integer positions and parked in scratch; k_normal_estimate then gathers one float4 per
+//     incident face instead of three indices and nine coordinates — this kernel waits on atomics anyway;
+//   * slot allocation in the per-vertex adjacency: one atomicAdd per face corner.  AGG (CORTO_ADJ_AGG=1) merges the lanes of a
+//     warp that name the same vertex in the same corner (match.any) into one atomic per group; it halves the atomics of a
+//     strip but the match + shuffle chain costs more than it saves on B200 (62 -> 92 us on 16 meshes), so it is off by default.
+template <bool AGG>
 __global__ void __launch_bounds__(256) k_adj_build(DevBatch B, const Tile *tiles, uint32_t ntiles) {
 	const Tile tl = tiles[blockIdx.x];
 	const MeshDesc *M = B.mesh + tl.a;
 	if(B.status[tl.a]) return;
 	const AdjView C = adj_view(M);
 	const bool border = M->attr[M->normal_attr].prediction == N_BORDER;
-	for(uint32_t f = tl.tile*SCAN_TILE + threadIdx.x; f < min(M->nface, (tl.tile + 1)*SCAN_TILE); f += 256) {
-		uint32_t v[3];
-		load_face(M, f, v[0], v[1], v[2]);
-		if(v[0] >= M->nvert || v[1] >= M->nvert || v[2] >= M->nvert) continue;
+	const int32_t *P = (const int32_t *)M->attr[M->position_attr].out_ptr;   // still integer (decoder.cpp:191-195)
+	const uint32_t FULL = 0xffffffffu, lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+	const uint32_t fend = min(M->nface, (tl.tile + 1)*SCAN_TILE);
+	for(uint32_t f0 = tl.tile*SCAN_TILE; f0 < fend; f0 += 256) {          // uniform trip count: the warp collectives below need every lane
+		const uint32_t f = f0 + threadIdx.x;
+		uint32_t v[3] = {0, 0, 0};
+		bool valid = f < fend;
+		if(valid) {
+			load_face(M, f, v[0], v[1], v[2]);
+			valid = v[0] < M->nvert && v[1] < M->nvert && v[2] < M->nvert;
+		}
+		if(valid) {
+			const float v0x = i2f(P[(size_t)v[0]*3]), v0y = i2f(P[(size_t)v[0]*3 + 1]), v0z = i2f(P[(size_t)v[0]*3 + 2]);
+			const float ax = f_sub(i2f(P[(size_t)v[1]*3]), v0x), ay = f_sub(i2f(P[(size_t)v[1]*3 + 1]), v0y), az = f_sub(i2f(P[(size_t)v[1]*3 + 2]), v0z);
+			const float bx = f_sub(i2f(P[(size_t)v[2]*3]), v0x), by = f_sub(i2f(P[(size_t)v[2]*3 + 1]), v0y), bz = f_sub(i2f(P[(size_t)v[2]*3 + 2]), v0z);
+			C.fn[f] = make_float4(f_sub(f_mul(ay, bz), f_mul(az, by)), f_sub(f_mul(az, bx), f_mul(ax, bz)), f_sub(f_mul(ax, by), f_mul(ay, bx)), 0.f);   // point.h:113-115
+		}
 #pragma unroll
 		for(int k = 0; k < 3; k++) {
-			const uint32_t s = atomicAdd(C.cnt + v[k], 1u);
-			if(s < 8) C.adj8[(size_t)v[k]*8 + s] = f;
-			else C.ovf[atomicAdd(C.novf, 1u)] = make_uint2(v[k], f);
+			uint32_t s = 0;
+			if constexpr(AGG) {
+				const uint32_t grp = __match_any_sync(FULL, valid ? v[k] : 0xffffffffu - lane);   // invalid lanes: singletons
+				const uint32_t leader = (uint32_t)__ffs(grp) - 1u;
+				uint32_t base = 0;
+				if(valid && lane == leader) base = atomicAdd(C.cnt + v[k], (uint32_t)__popc(grp));
+				s = __shfl_sync(FULL, base, leader) + (uint32_t)__popc(grp & below);
+			} else if(valid) s = atomicAdd(C.cnt + v[k], 1u);
+			if(valid) {
+				if(s < 8) C.adj8[(size_t)v[k]*8 + s] = f;
+				else C.ovf[atomicAdd(C.novf, 1u)] = make_uint2(v[k], f);
+			}
 		}
-		if(border) { atomicXor(C.bnd + v[0], v[1] ^ v[2]); atomicXor(C.bnd + v[1], v[2] ^ v[0]); atomicXor(C.bnd + v[2], v[0] ^ v[1]); }   // markBoundary :24-37
+		if(border && valid) { atomicXor(C.bnd + v[0], v[1] ^ v[2]); atomicXor(C.bnd + v[1], v[2] ^ v[0]); atomicXor(C.bnd + v[2], v[0] ^ v[1]); }   // markBoundary :24-37
 	}
 }
 
@@ -1048,22 +1092,15 @@ __global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile 
 	if(B.status[tl.a]) return;
 	const AdjView C = adj_view(M);
 	const AttrDesc *A = &M->attr[M->normal_attr];
-	const int32_t *P = (const int32_t *)M->attr[M->position_attr].out_ptr;   // still integer (decoder.cpp:191-195)
 	const int32_t *diffs = (const int32_t *)A->work_ptr;
 	const int unit = f2i_x86(A->q);
 	const bool border = A->prediction == N_BORDER;
 	for(uint32_t i = tl.tile*SCAN_TILE + threadIdx.x; i < min(M->nvert, (tl.tile + 1)*SCAN_TILE); i += 256) {
 		const uint32_t deg = C.cnt[i];
 		float ex = 0.f, ey = 0.f, ez = 0.f;
-		auto add_face = [&](uint32_t f) {                              // estimateNormals :44-55, one corner's worth
-			uint32_t a, b, c;
-			load_face(M, f, a, b, c);
-			const float v0x = i2f(P[(size_t)a*3]), v0y = i2f(P[(size_t)a*3 + 1]), v0z = i2f(P[(size_t)a*3 + 2]);
-			const float ax = f_sub(i2f(P[(size_t)b*3]), v0x), ay = f_sub(i2f(P[(size_t)b*3 + 1]), v0y), az = f_sub(i2f(P[(size_t)b*3 + 2]), v0z);
-			const float bx = f_sub(i2f(P[(size_t)c*3]), v0x), by = f_sub(i2f(P[(size_t)c*3 + 1]), v0y), bz = f_sub(i2f(P[(size_t)c*3 + 2]), v0z);
-			ex = f_add(ex, f_sub(f_mul(ay, bz), f_mul(az, by)));      // point.h:113-115
-			ey = f_add(ey, f_sub(f_mul(az, bx), f_mul(ax, bz)));
-			ez = f_add(ez, f_sub(f_mul(ax, by), f_mul(ay, bx)));
+		auto add_face = [&](uint32_t f) {                              // estimateNormals :44-55, one corner's worth (cross product: k_adj_build)
+			const float4 n = C.fn[f];
+			ex = f_add(ex, n.x); ey = f_add(ey, n.y); ez = f_add(ez, n.z);
 		};
 		if(deg <= 8) {
 			// the usual case: sort the (at most 8) incident faces in registers, add in ascending face order
@@ -1477,7 +1514,10 @@ int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cuda
 }
 int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_adj_build<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	static int agg = -1;
+	if(agg < 0) { const char *e = getenv("CORTO_ADJ_AGG"); agg = (e && e[0] == '1') ? 1 : 0; }
+	if(agg) k_adj_build<true><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	else k_adj_build<false><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {

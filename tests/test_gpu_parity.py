@@ -96,7 +96,7 @@ def test_tarta():
             _same("tarta/" + k, got[k], w)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "split0", "split1", "overlap1", "adjagg1"])
 def test_alternative_clers_machines(mode, tmp_path):
     """CORTO_CLERS=1 (single-warp lazy-front machine) and =2 (leader/follower without window steps) stay bit-exact: they are the
     A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
@@ -117,5 +117,14 @@ for path in sorted(glob.glob(os.path.join(%r, "*.crt"))):
             assert np.array_equal(got[k].view(np.uint8).reshape(-1), w.view(np.uint8).reshape(-1)), (path, k)
 print("ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")))
-    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, CORTO_CLERS=mode), capture_output=True, text=True, timeout=300)
+    # split0 / split1: the delta inverse with one warp per (mesh, attribute) / per component (the host picks by batch size);
+    # overlap3: the side-stream stage overlap (CORTO_OVERLAP, off by default)
+    extra = {"CORTO_CLERS": mode}
+    if mode.startswith("split"):
+        extra = {"CORTO_DELTA_SPLIT": mode[-1]}
+    elif mode.startswith("overlap"):
+        extra = {"CORTO_OVERLAP": mode[-1]}
+    elif mode.startswith("adjagg"):
+        extra = {"CORTO_ADJ_AGG": mode[-1]}       # warp-aggregated adjacency atomics (off by default)
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
