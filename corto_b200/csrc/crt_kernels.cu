@@ -454,44 +454,44 @@ __device__ uint32_t lead_vector(const ClersIO &io, SmemRings4 &rg, LeadState &S,
 		if(lim < 2) break;
 		uint32_t sym = pre.sym;
 		if(pre.at != cler) sym = cler + lane < io.nclers ? (uint32_t)io.clers[cler + lane] : 0xffu;
+		// Fast path for the prev chain: the edges a strip consumes on its left are usually the queued edges of ONE earlier strip,
+		// created back to back and linked in creation order (prev of id k is k+1).  Every lane checks one link; if all of them
+		// hold the chain is prev, prev+1, ... and nothing is walked.  Any mismatch falls back to the serial walk.  The link is
+		// loaded first thing (it only depends on `prev`), so its latency hides behind the symbol ballots.
+		const uint32_t idk = prev + lane;
+		uint32_t pk = 0xffffffffu, pn;
+		if(idk >= eflush && idk < nfront && idk != next) rg.ldB(idk, pk, pn);
 		const bool isV = lane < lim && sym == C_VERTEX, isL = lane < lim && sym == C_LEFT;
-		const uint32_t stop = __ballot_sync(FULL, !(isV || isL));
+		const uint32_t bV = __ballot_sync(FULL, isV), bL = __ballot_sync(FULL, isL);
+		const uint32_t stop = ~(bV | bL);
 		const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
 		if(m < 2) { pre.at = cler; pre.sym = sym; break; }
 		pre.at = cler + m;                                 // the usual case: the run goes on right behind this window
 		pre.sym = pre.at + lane < io.nclers ? (uint32_t)io.clers[pre.at + lane] : 0xffu;
 		const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
-		const uint32_t Vm = __ballot_sync(FULL, isV) & pm, Lm = __ballot_sync(FULL, isL) & pm;
+		const uint32_t Vm = bV & pm, Lm = bL & pm;
 		const uint32_t nV = __popc(Vm), nL = __popc(Lm);
 		if(nfront + nV > io.cap) break;                    // the scalar machine flags it
-		// Fast path for the prev chain: the edges a strip consumes on its left are usually the queued edges of ONE earlier strip,
-		// created back to back and linked in creation order (prev of id k is k+1).  Every lane checks one link; if all of them
-		// hold the chain is prev, prev+1, ... and nothing is walked.  Any mismatch falls back to the serial walk.
 		uint32_t p = prev + __popc(Lm & below), newprev = prev + nL;
-		if(nL) {
-			const uint32_t idk = prev + lane;
-			uint32_t pk = 0xffffffffu, pn;
-			if(lane < nL && idk >= eflush && idk < nfront && idk != next) rg.ldB(idk, pk, pn);
-			if(!__all_sync(FULL, lane >= nL || pk == idk + 1)) {
-				uint32_t ok = 1;
-				if(lane == 0) {
-					uint32_t q = prev;
-					for(uint32_t k = 0; k < nL; k++) {         // the serial part: walk the prev chain
-						chain[k] = q;
-						if(q == next) ok = 0;                  // the walk wraps around to the right-hand neighbour (small loop): its links
-						                                       // change inside this window, so take the scalar path
-						uint32_t pp, pq;
-						if(q >= eflush) rg.ldB(q, pp, pq); else { const uint2_t t_ = lead_g_load(io.eb, q); pp = t_.x; pq = t_.y; }
-						(void)pq;
-						q = pp;
-					}
-					chain[nL] = q;
+		if(!__all_sync(FULL, lane >= nL || pk == idk + 1)) {
+			uint32_t ok = 1;
+			if(lane == 0) {
+				uint32_t q = prev;
+				for(uint32_t k = 0; k < nL; k++) {             // the serial part: walk the prev chain
+					chain[k] = q;
+					if(q == next) ok = 0;                      // the walk wraps around to the right-hand neighbour (small loop): its links
+					                                           // change inside this window, so take the scalar path
+					uint32_t pp, pq;
+					if(q >= eflush) rg.ldB(q, pp, pq); else { const uint2_t t_ = lead_g_load(io.eb, q); pp = t_.x; pq = t_.y; }
+					(void)pq;
+					q = pp;
 				}
-				__syncwarp();
-				ok = __shfl_sync(FULL, ok, 0);
-				if(!ok) break;
-				p = chain[__popc(Lm & below)]; newprev = chain[nL];
+				chain[nL] = q;
 			}
+			__syncwarp();
+			ok = __shfl_sync(FULL, ok, 0);
+			if(!ok) break;
+			p = chain[__popc(Lm & below)]; newprev = chain[nL];
 		}
 		if(lane < m) {                                     // one flag byte and one log word per lane, whatever the symbol
 			const uint32_t r = __popc(Vm & below), b = nfront + r;
@@ -585,26 +585,28 @@ __device__ uint32_t follow_vector(const ClersIO &io, SmemRings4 &rg, FollowState
 		const uint32_t w = lane < lim ? rg.ldLog(tail + lane) : 0xffffffffu;
 		const uint32_t t = w >> 28, id = w & 0x0FFFFFFFu;
 		const bool isV = t == LG_V, isL = t == LG_L;
-		uint32_t stop = __ballot_sync(FULL, !(isV || isL));
+		// the label a LEFT consumes is loaded at once, for every LEFT word in sight (harmless past the end of the window: ids in
+		// the log are valid ring / scratch indices), so that its latency hides behind the ballots that find the window end
+		uint32_t a = 0;
+		if(isL) {
+			uint32_t t1, t2;
+			if(id >= aflush) rg.ldA(id, a, t1, t2); else { const uint4_t g_ = follow_g_load(io.ea, id); a = g_.x; }
+		}
+		const uint32_t vall = __ballot_sync(FULL, isV), lall = __ballot_sync(FULL, isL);
+		uint32_t stop = ~(vall | lall);
 		// a LEFT may consume an edge that a VERTEX of this very window creates (the prev chain wrapped around a small loop): its
 		// label does not exist yet, so the window ends in front of it.  Ids grow with creation order: compare with the first V's.
-		const uint32_t vall = __ballot_sync(FULL, isV);
 		const uint32_t firstid = __shfl_sync(FULL, id, vall ? __ffs(vall) - 1 : 0);
 		stop |= __ballot_sync(FULL, isL && vall && id >= firstid && (uint32_t)(__ffs(vall) - 1) < lane);
 		const uint32_t m = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
 		if(m < 2) break;
 		const uint32_t pm = m == 32 ? FULL : ((1u << m) - 1u);
-		const uint32_t Vm = vall & pm, Lm = __ballot_sync(FULL, isL) & pm;
+		const uint32_t Vm = vall & pm, Lm = lall & pm;
 		const uint32_t nV = __popc(Vm);
 		if(vcount + nV > io.nvert || nf + m > io.nface) break;          // let the scalar machine flag the error
 		if(!done) {                                                     // first window of this call: flush what the scalar machine staged
 			const uint32_t f0 = __shfl_sync(FULL, F.fflush, 0), p0 = __shfl_sync(FULL, F.pflush, 0);
 			if(f0 != nf || p0 != vcount) follow_drain(io, rg, oF, oP, f0, nf, p0, vcount, lane);
-		}
-		uint32_t a = 0;
-		if(lane < m && isL) {
-			uint32_t t1, t2;
-			if(id >= aflush) rg.ldA(id, a, t1, t2); else { const uint4_t g_ = follow_g_load(io.ea, id); a = g_.x; }
 		}
 		// who defined v0 / v1 last before this lane: v1 is a count (vertex ids are consecutive), v0 needs the label of the last LEFT
 		const uint32_t lLT = Lm & lt, vLT = Vm & lt, vLT1 = Vm & (lt >> 1);
