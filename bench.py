@@ -47,7 +47,7 @@ def parse():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_clers_lf per c2 mesh (profiles/r1_k_clers_lf_ncu_raw.txt: 16 meshes)
-TRAFFIC_CLERS_C2_PER_MESH = int((4.685056e6 + 71.896832e6) / 16)
+TRAFFIC_CLERS_C2_PER_MESH = int((4.281856e6 + 73.254656e6) / 16)
 
 DEFAULT_BATCH = dict(c1=1, c2=256, c3=512, c4=512, c5=1, tarta=64)
 
@@ -228,8 +228,8 @@ def main():
     roof = None
     if dom:
         ach = (in_bytes + out_bytes) / (stage_ms[dom] * 1e-3) / 1e9
-        kernel_of = {"clers": "k_clers_lf", "delta": "k_delta_mesh / k_delta_cloud", "cloud_fused": "k_cloud_fused", "tun_decode": "k_tun_decode",
-                     "bit_unpack": "k_bit_unpack", "normals": "k_csr_* + k_normal_estimate", "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
+        kernel_of = {"clers": "k_clers_lf", "delta": "k_delta_mesh", "cloud_fused": "k_unpack_fused<CLOUD>", "tun_decode": "k_tun_decode",
+                     "bit_unpack": "k_unpack_fused<MESH>", "normals": "k_adj_build + k_normal_estimate", "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/): measured per mesh on a 16-mesh
         # batch of this workload, scaled to this batch; null where no capture exists for the kernel/workload pair
         traffic = None
