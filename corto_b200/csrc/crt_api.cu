@@ -430,8 +430,11 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	// Delta work items: one warp per (mesh, attribute) walks all components together (they share the prediction loads and
 	// interleave in the pipeline).  When that leaves most SMs without a warp (few, large meshes) the components — independent
 	// chains — get a warp each instead: measured 94 -> 80 ms on 64 x 1.7 M-vertex meshes, no gain (c2) or a loss (c4) on big batches.
+	// (only the default warp kernel takes per-component items; the block-wide kernel, CORTO_DELTA=cta|seq, walks all components)
 	const char *force = getenv("CORTO_DELTA_SPLIT");                // 0 / 1 overrides the heuristic (tests, A/B runs)
-	if(force ? force[0] == '1' : b->w_delta.size() < 2u*(size_t)b->sms) {
+	const char *dmode = getenv("CORTO_DELTA");
+	const bool warp_kernel = !(dmode && (dmode[0] == 'c' || dmode[0] == 's'));
+	if(warp_kernel && (force ? force[0] == '1' : b->w_delta.size() < 2u*(size_t)b->sms)) {
 		std::vector<uint2> split;
 		for(const uint2 &w: b->w_delta)
 			for(unsigned c = 0; c < (w.y >> 16); c++) split.push_back(make_uint2(w.x, (w.y & 0xffu) | (c << 8)));

@@ -944,6 +944,235 @@ __device__ __forceinline__ void delta_mesh_rounds(T *v, const uint32_t stride, c
 	}
 }
 
+// ---- block-wide rounds (experiment switch CORTO_DELTA=cta; not the default, see launch_delta_mesh) -----------------------------
+// The warp kernel above walks a (mesh, attribute) chain 32 vertices at a time, ~220 dependent instructions per round, 4096
+// rounds for a 128 K-vertex mesh whatever the batch size.  Here one CTA of 256 threads takes 256 vertices per round,
+// thread = vertex:
+//   * loads (prediction, residual, operands that are final in global memory) are issued one round ahead; operands inside the
+//     PREVIOUS round are read from its finals in shared memory (two buffers);
+//   * operands inside the round: the round is cut into SUB-BLOCKS [s, e) such that no vertex of a sub-block has a `b` / `c`
+//     operand inside it (e = the first vertex naming something at or after s).  Inside a sub-block only `a` links remain, a
+//     forest with parents at lower indices: log2(e - s) pointer-doubling steps through shared memory; `b` / `c` (and `a`) that
+//     point into earlier sub-blocks read finals from the round's buffer.  A strip of a regular mesh is one sub-block (the
+//     previous row lies a whole strip back), so a round costs ~12-20 barrier-separated steps instead of 8 x 220 dependent
+//     instructions — but each such step (shared-memory write, barrier, dependent shared-memory read) measures ~400-500 cycles
+//     with the next round's loads in flight, which is why this is not faster than the warp kernel yet (next: in-warp shuffle
+//     doubling for the first five steps, a second round of prefetch);
+//   * a sub-block shorter than 4 vertices (irregular meshes: the parallelogram names the vertices created just before) or an
+//     operand naming its own or a later vertex (hostile streams) sends the rest of the round to the 8 warps one after the
+//     other with the warp algorithm (warp_resolve), which reads the finals of the vertices before it — and the residuals of
+//     the vertices after it, which is what the in-place reference loop would read — from the same buffer.
+// Same in-place semantics as vertex_attribute.h:165-176 / normal_attribute.cpp:193-201 for every input.
+template <int NC>
+__device__ __forceinline__ void warp_resolve(uint32_t (&x)[NC], const uint32_t (&resid)[NC], const uint32_t (&fa)[NC], const uint32_t (&fb)[NC], const uint32_t (&fc)[NC],
+                                             bool act, bool a_in, bool b_in, bool c_in, uint32_t wa, uint32_t wb, uint32_t wc, uint32_t lane) {
+	// x: in  = residual + the contributions from outside the round (act lanes) / the final value (lanes that are done);  out = final
+	// resid: the bare residual (what an operand naming this or a later lane reads);  fa / fb / fc: contributions of the in-round
+	// operands that are NOT inside this warp's 32 vertices (0 when inside or unused)
+	const uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
+	const bool tree_ok = !act || (!b_in && !c_in && (!a_in || wa < lane));
+	if(__all_sync(FULL, tree_ok)) {
+		uint32_t parent = (act && a_in) ? wa : NONE;
+		uint32_t r[NC];
+#pragma unroll
+		for(int k = 0; k < NC; k++) r[k] = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k];
+#pragma unroll
+		for(int d = 0; d < 5; d++) {
+			const uint32_t src = parent == NONE ? lane : parent;
+			const uint32_t pp = __shfl_sync(FULL, parent, src);
+#pragma unroll
+			for(int k = 0; k < NC; k++) { const uint32_t pr = __shfl_sync(FULL, r[k], src); if(parent != NONE) r[k] += pr; }
+			if(parent != NONE) parent = pp;
+		}
+#pragma unroll
+		for(int k = 0; k < NC; k++) x[k] = r[k];
+	} else {
+		const uint32_t la = (act && a_in) ? wa : 64u, lb = (act && b_in) ? wb : 64u, lc = (act && c_in) ? wc : 64u;
+		uint32_t acc[NC], res[NC];
+#pragma unroll
+		for(int k = 0; k < NC; k++) { res[k] = resid[k]; acc[k] = act ? x[k] + fa[k] + fb[k] - fc[k] : x[k]; }
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			const uint32_t qa = __shfl_sync(FULL, res[k], la & 31u), qb = __shfl_sync(FULL, res[k], lb & 31u), qc = __shfl_sync(FULL, res[k], lc & 31u);
+			if(la < 32u && la >= lane) acc[k] += qa;       // an operand naming this or a HIGHER lane reads that lane's residual
+			if(lb < 32u && lb >= lane) acc[k] += qb;
+			if(lc < 32u && lc >= lane) acc[k] -= qc;
+		}
+		const uint32_t named = __reduce_or_sync(FULL, (la < lane ? 1u << la : 0u) | (lb < lane ? 1u << lb : 0u) | (lc < lane ? 1u << lc : 0u));
+		for(uint32_t todo = named; todo; todo &= todo - 1) {
+			const uint32_t j = (uint32_t)__ffs(todo) - 1u;     // every lane below j that anyone names has been pushed already: acc of lane j is final
+#pragma unroll
+			for(int k = 0; k < NC; k++) {
+				const uint32_t xj = __shfl_sync(FULL, acc[k], j);
+				if(la == j) acc[k] += xj;
+				if(lb == j) acc[k] += xj;
+				if(lc == j) acc[k] -= xj;
+			}
+		}
+#pragma unroll
+		for(int k = 0; k < NC; k++) x[k] = acc[k];
+	}
+}
+
+constexpr uint32_t DB = 256;           // vertices per block-wide round
+constexpr uint32_t DB_MINSUB = 4;      // a shorter sub-block sends the rest of the round to the sequential warps
+template <typename T, int NC>
+__device__ __forceinline__ void delta_mesh_cta(T *v, const uint4 *pred, const uint32_t nvert, const bool par, const bool force_seq,
+                                               uint32_t *s_fin /*[2][DB][NC]*/, uint32_t *s_r /*[2][DB][NC]*/, uint32_t *s_par /*[2][DB]*/, uint32_t *s_min /*[8]*/) {
+	const uint32_t NONE = 0xffffffffu, FULL = 0xffffffffu;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t nblk = (nvert + DB - 1u)/DB;
+	// registers of the round being resolved (C) and of the next one (N)
+	uint4 pC = make_uint4(0, 0, 0, 0), pN;
+	uint32_t xC[NC], gaC[NC], gbC[NC], gcC[NC], xN[NC], gaN[NC], gbN[NC], gcN[NC];
+	auto load_round = [&](uint32_t r, uint4 &p, uint32_t (&x)[NC], uint32_t (&ga)[NC], uint32_t (&gb)[NC], uint32_t (&gc)[NC]) {
+		const uint32_t base = r*DB, i = base + tid;
+		const bool in = r < nblk && i < nvert, act = in && i > 0;
+		p = in ? pred[i] : make_uint4(0, 0, 0, 0);
+		auto far = [&](uint32_t X, bool use, uint32_t (&g)[NC]) {
+			// final in global memory (rounds < r-1), or a residual nobody has touched yet (rounds > r: hostile streams only)
+			const bool prevblk = r > 0 && X - (base - DB) < DB, inblk = X - base < DB;
+#pragma unroll
+			for(int k = 0; k < NC; k++) g[k] = (use && !prevblk && !inblk && X < nvert) ? (uint32_t)v[(size_t)X*NC + k] : 0u;
+		};
+#pragma unroll
+		for(int k = 0; k < NC; k++) x[k] = in ? (uint32_t)v[(size_t)i*NC + k] : 0u;
+		far(p.x, act, ga); far(p.y, act && par, gb); far(p.z, act && par, gc);
+	};
+	load_round(0, pC, xC, gaC, gbC, gcC);
+	uint32_t q = 0;                                        // pointer-doubling step counter (buffer parity), never reset
+	for(uint32_t r = 0; r < nblk; r++) {
+		const uint32_t cur = r & 1u, prv = cur ^ 1u;
+		const uint32_t base = r*DB, i = base + tid;
+		const bool in = i < nvert, act = in && i > 0;       // vertex 0 keeps its residual (loops start at 1)
+		load_round(r + 1, pN, xN, gaN, gbN, gcN);             // in flight while this round resolves
+		const uint32_t a = pC.x, b = pC.y, c = pC.z;
+		const bool usebc = act && par;
+		const bool a_prev = act && r > 0 && a - (base - DB) < DB, b_prev = usebc && r > 0 && b - (base - DB) < DB, c_prev = usebc && r > 0 && c - (base - DB) < DB;
+		const bool a_in = act && a - base < DB, b_in = usebc && b - base < DB, c_in = usebc && c - base < DB;
+		const uint32_t la = (a - base) & (DB - 1u), lb = (b - base) & (DB - 1u), lc = (c - base) & (DB - 1u);
+		uint32_t *fin_c = s_fin + (size_t)cur*DB*NC, *fin_p = s_fin + (size_t)prv*DB*NC;
+		// x: residual + every contribution from outside the round
+		uint32_t x[NC];
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			const uint32_t fa = a_prev ? fin_p[((a - (base - DB)) & (DB - 1u))*NC + k] : gaC[k];      // (0 when inside the round or unused)
+			const uint32_t fb = b_prev ? fin_p[((b - (base - DB)) & (DB - 1u))*NC + k] : gbC[k];
+			const uint32_t fc = c_prev ? fin_p[((c - (base - DB)) & (DB - 1u))*NC + k] : gcC[k];
+			fin_c[tid*NC + k] = xC[k];                        // until it is final a vertex shows its residual, as in the in-place loop
+			x[k] = act ? xC[k] + fa + fb - fc : xC[k];
+		}
+		// an operand naming its own or a later vertex of the round: only the sequential order gives the reference's answer
+		const bool hostile = (a_in && la >= tid) || (b_in && lb >= tid) || (c_in && lc >= tid);
+		uint32_t s = __syncthreads_or(hostile || force_seq) ? 0u : DB + 1u;      // DB + 1: no fallback requested (yet)
+		if(s > DB) {
+			const int mbc = max(b_in ? (int)lb : -1, c_in ? (int)lc : -1);       // the last in-round vertex my b / c name
+			uint32_t parent0 = a_in ? la : NONE;
+			uint32_t s0 = 0;
+			while(s0 < DB) {
+				// e = first vertex >= s0 that names (b / c) something at or after s0
+				const uint32_t cand = __ballot_sync(FULL, tid >= s0 && mbc >= (int)s0);
+				if(lane == 0) s_min[warp] = cand ? warp*32u + (uint32_t)__ffs(cand) - 1u : DB;
+				__syncthreads();
+				uint32_t e = DB;
+#pragma unroll
+				for(int w8 = 0; w8 < (int)(DB/32u); w8++) e = min(e, s_min[w8]);
+				if(e - s0 < DB_MINSUB && DB - s0 > 32u) { s = s0; break; }           // irregular stretch: sequential warps from s0 on
+				const bool mine = tid >= s0 && tid < e;
+				uint32_t parent = NONE;
+				if(mine) {
+#pragma unroll
+					for(int k = 0; k < NC; k++) {
+						if(b_in) x[k] += fin_c[lb*NC + k];            // earlier sub-blocks: final
+						if(c_in) x[k] -= fin_c[lc*NC + k];
+						if(a_in && la < s0) x[k] += fin_c[la*NC + k];
+					}
+					if(a_in && la >= s0) parent = parent0;
+				}
+				for(uint32_t span = 1; span < e - s0; span <<= 1, q++) {
+					uint32_t *rr = s_r + (size_t)(q & 1u)*DB*NC, *pp = s_par + (q & 1u)*DB;
+					if(mine) {
+						pp[tid] = parent;
+#pragma unroll
+						for(int k = 0; k < NC; k++) rr[tid*NC + k] = x[k];
+					}
+					__syncthreads();
+					if(parent != NONE) {
+#pragma unroll
+						for(int k = 0; k < NC; k++) x[k] += rr[parent*NC + k];
+						parent = pp[parent];
+					}
+				}
+				if(mine) {
+#pragma unroll
+					for(int k = 0; k < NC; k++) fin_c[tid*NC + k] = x[k];
+				}
+				__syncthreads();
+				s0 = e;
+			}
+		}
+		if(s <= DB) {
+			// sequential warps over [s, DB): vertices below s are final (their x is the final value and they take no further part)
+#pragma unroll 1
+			for(uint32_t ws = s >> 5; ws < DB/32u; ws++) {
+				if(warp == ws) {
+					const bool todo = act && tid >= s;
+					const bool wa_in = a_in && (la >> 5) == ws, wb_in = b_in && (lb >> 5) == ws, wc_in = c_in && (lc >> 5) == ws;
+					uint32_t ga2[NC], gb2[NC], gc2[NC];
+#pragma unroll
+					for(int k = 0; k < NC; k++) {           // in the round but outside this warp: final (before) or residual (after)
+						ga2[k] = (a_in && !wa_in) ? fin_c[la*NC + k] : 0u;
+						gb2[k] = (b_in && !wb_in) ? fin_c[lb*NC + k] : 0u;
+						gc2[k] = (c_in && !wc_in) ? fin_c[lc*NC + k] : 0u;
+					}
+					warp_resolve<NC>(x, xC, ga2, gb2, gc2, todo, wa_in, wb_in, wc_in, la & 31u, lb & 31u, lc & 31u, lane);
+#pragma unroll
+					for(int k = 0; k < NC; k++) fin_c[tid*NC + k] = x[k];
+				}
+				__syncthreads();
+			}
+		}
+		if(act) {
+#pragma unroll
+			for(int k = 0; k < NC; k++) v[(size_t)i*NC + k] = (T)x[k];
+		}
+		__syncthreads();                                   // finals of this round (shared and global) before the next round reads them
+		pC = pN;
+#pragma unroll
+		for(int k = 0; k < NC; k++) { xC[k] = xN[k]; gaC[k] = gaN[k]; gbC[k] = gbN[k]; gcC[k] = gcN[k]; }
+	}
+}
+
+__global__ void __launch_bounds__(256) k_delta_mesh_cta(DevBatch B, const uint2 *work, uint32_t nwork, bool force_seq) {
+	__shared__ uint32_t s_fin[2*DB*MAX_COMP], s_r[2*DB*MAX_COMP], s_par[2*DB], s_min[DB/32];
+	const uint32_t w = blockIdx.x;
+	if(w >= nwork) return;
+	const MeshDesc *M = B.mesh + work[w].x;
+	const AttrDesc *A = &M->attr[work[w].y & 0xffu];
+	if(B.status[work[w].x]) return;
+	const uint32_t nvert = M->nvert;
+	const uint4 *pred = (const uint4 *)M->pred_ptr;
+	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;    // normals: d += d[a] only (normal_attribute.cpp:193-201)
+	if(A->codec == CODEC_COLOR) {
+		uint8_t *v = (uint8_t *)A->work_ptr;
+		switch(A->ncomp) {
+		case 1: delta_mesh_cta<uint8_t, 1>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		case 2: delta_mesh_cta<uint8_t, 2>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		case 3: delta_mesh_cta<uint8_t, 3>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		default: delta_mesh_cta<uint8_t, 4>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		}
+	} else {
+		uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
+		switch(A->ncomp) {
+		case 1: delta_mesh_cta<uint32_t, 1>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		case 2: delta_mesh_cta<uint32_t, 2>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		case 3: delta_mesh_cta<uint32_t, 3>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		default: delta_mesh_cta<uint32_t, 4>(v, pred, nvert, par, force_seq, s_fin, s_r, s_par, s_min); break;
+		}
+	}
+}
+
+// The default: one warp per chain.
 __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work, uint32_t nwork) {
 	const uint32_t w = blockIdx.x;
 	if(w >= nwork) return;
@@ -1511,7 +1740,14 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 }
 int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cudaStream_t s) {
 	if(nwork == 0) return 0;
-	k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
+	// default: one warp per chain (k_delta_mesh; the host may have split the work list per component).  CORTO_DELTA=cta: one CTA
+	// per (mesh, attribute), 256 vertices per round (k_delta_mesh_cta) — measured 2.51 vs 2.40 ms on configs[1], 8.7 vs 6.5 ms on
+	// configs[3], 110 vs 80 ms on 64 x tarta, so it is an experiment switch, not the default; CORTO_DELTA=seq: the same kernel with
+	// every round on its sequential-warp path (tests).
+	static int mode = -1;
+	if(mode < 0) { const char *e = getenv("CORTO_DELTA"); mode = (e && e[0] == 'c') ? 0 : ((e && e[0] == 's') ? 2 : 1); }
+	if(mode == 1) k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
+	else k_delta_mesh_cta<<<nwork, 256, 0, s>>>(B, work, nwork, mode == 2);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {

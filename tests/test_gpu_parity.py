@@ -96,7 +96,7 @@ def test_tarta():
             _same("tarta/" + k, got[k], w)
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "split0", "split1", "overlap1", "adjagg1"])
+@pytest.mark.parametrize("mode", ["1", "2", "split0", "split1", "deltacta", "deltaseq", "overlap1", "adjagg1"])
 def test_alternative_clers_machines(mode, tmp_path):
     """CORTO_CLERS=1 (single-warp lazy-front machine) and =2 (leader/follower without window steps) stay bit-exact: they are the
     A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
@@ -118,10 +118,14 @@ for path in sorted(glob.glob(os.path.join(%r, "*.crt"))):
 print("ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")))
     # split0 / split1: the delta inverse with one warp per (mesh, attribute) / per component (the host picks by batch size);
-    # overlap3: the side-stream stage overlap (CORTO_OVERLAP, off by default)
+    # overlap1: the side-stream stage overlap (CORTO_OVERLAP, off by default)
     extra = {"CORTO_CLERS": mode}
-    if mode.startswith("split"):
+    if mode.startswith("split"):                  # the warp-per-chain delta kernel, per (mesh, attribute) / per component
         extra = {"CORTO_DELTA_SPLIT": mode[-1]}
+    elif mode == "deltacta":                      # the block-wide delta kernel (sub-blocks + pointer doubling through shared memory)
+        extra = {"CORTO_DELTA": "cta"}
+    elif mode == "deltaseq":                      # ... with every round on its sequential-warp path
+        extra = {"CORTO_DELTA": "seq"}
     elif mode.startswith("overlap"):
         extra = {"CORTO_OVERLAP": mode[-1]}
     elif mode.startswith("adjagg"):
