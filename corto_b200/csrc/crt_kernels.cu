@@ -1448,7 +1448,7 @@ template <int NC> __device__ __forceinline__ void cta_scan_multi(const uint32_t 
 
 template <int NC, bool MESH>
 __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M, const AttrDesc *A, const Tile &tl, uint32_t tile_id, uint64_t *states,
-                                           uint32_t (*s_w)[9], uint64_t *s_base, uint8_t *s_out) {
+                                           uint32_t (*s_w)[9], uint64_t *s_base, uint8_t *s_out, uint64_t *s_carry = nullptr) {
 	const int tid = threadIdx.x;
 	const uint32_t nvert = M->nvert;
 	const bool correlated = (A->codec == CODEC_NORMAL) || (A->codec == CODEC_GENERIC && (A->strategy & S_CORRELATED));
@@ -1484,7 +1484,12 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 	if(correlated) bits[0] *= (uint32_t)NC;
 	uint32_t bexcl[NC], btot[NC];
 	cta_scan_multi<NC>(bits, bexcl, btot, s_w);
-	if(tid < (correlated ? 1 : NC)) s_base[tid] = lookback_strided(states, tile_id, 8, (uint32_t)tid, first, btot[tid]);
+	if(tid < (correlated ? 1 : NC)) {
+		// bit offset of this tile inside each log stream: the running total when one CTA walks the whole chain (k_unpack_chain),
+		// a decoupled look-back over the predecessors' totals when the tiles of a chain are spread over CTAs
+		if(s_carry) { s_base[tid] = s_carry[tid]; s_carry[tid] += btot[tid]; }
+		else s_base[tid] = lookback_strided(states, tile_id, 8, (uint32_t)tid, first, btot[tid]);
+	}
 	__syncthreads();
 	// ---- unpack the residuals of my 4 vertices ----
 	uint32_t r[NC][4];
@@ -1638,6 +1643,36 @@ __global__ void __launch_bounds__(256) k_unpack_fused(DevBatch B, const Tile *ti
 	}
 }
 
+// The same tiles, one CTA per CHAIN (all tiles of one attribute of one mesh, in order): the bit offsets are a running total in
+// shared memory, so there is no ticket, no look-back and nobody spins on a predecessor (in k_unpack_fused 10.5 of every 24
+// stall cycles are the other 255 threads waiting at the barrier behind the look-back thread).  Used when the batch has enough
+// chains to fill the GPU; heads[c] .. heads[c+1] are the chain's tiles in the tile list.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_unpack_chain(DevBatch B, const Tile *tiles, const uint32_t *heads, uint32_t nchains) {
+	__shared__ uint32_t s_w[4][9];
+	__shared__ uint64_t s_base[4], s_carry[4];
+	__shared__ __align__(16) uint8_t s_out[1024*16];
+	const uint32_t c = blockIdx.x;
+	if(c >= nchains) return;
+	if(threadIdx.x < 4) s_carry[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t t0 = heads[c], t1 = heads[c + 1];
+	Tile tl = tiles[t0];
+	const MeshDesc *M = B.mesh + tl.a;
+	const AttrDesc *A = &M->attr[tl.b];
+	const int nc = A->ncomp;
+	for(uint32_t t = t0; t < t1; t++) {
+		tl.tile = t - t0; tl.first = t == t0 ? 1u : 0u;
+		switch(nc) {
+		case 1: cloud_tile<1, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		case 2: cloud_tile<2, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		case 3: cloud_tile<3, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		default: cloud_tile<4, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		}
+		__syncthreads();                             // s_w / s_base / s_out are reused by the next tile
+	}
+}
+
 // =========================================================================================================
 // K7  dequantise.  tiles: a = mesh, b = attr, tile = block of SCAN_TILE vertices
 // =========================================================================================================
@@ -1773,9 +1808,17 @@ int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, ui
 	k_unpack_fused<false><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, const uint32_t *heads, uint32_t nchains, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_unpack_fused<true><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	// one CTA per chain when there are enough chains to fill the GPU (CORTO_UNPACK=chain / lookback forces either: tests, A/B runs)
+	static int mode = -1;
+	if(mode < 0) { const char *e = getenv("CORTO_UNPACK"); mode = (e && e[0] == 'c') ? 1 : ((e && e[0] == 'l') ? 2 : 0); }
+	const bool chain = mode == 1 || (mode == 0 && nchains >= 2u*(uint32_t)sms);
+	static int occ = -1;                  // CORTO_UNPACK_OCC=6: cap registers at 40 for 6 CTAs per SM (a few spills) instead of 5
+	if(occ < 0) { const char *e = getenv("CORTO_UNPACK_OCC"); occ = (e && e[0] == '6') ? 6 : 5; }
+	if(chain && occ == 6) k_unpack_chain<6><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+	else if(chain) k_unpack_chain<5><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+	else k_unpack_fused<true><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {

@@ -96,7 +96,7 @@ def test_tarta():
             _same("tarta/" + k, got[k], w)
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "split0", "split1", "deltacta", "deltaseq", "overlap1", "adjagg1"])
+@pytest.mark.parametrize("mode", ["1", "2", "split0", "split1", "deltacta", "deltaseq", "unpackchain", "overlap1", "adjagg1"])
 def test_alternative_clers_machines(mode, tmp_path):
     """CORTO_CLERS=1 (single-warp lazy-front machine) and =2 (leader/follower without window steps) stay bit-exact: they are the
     A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
@@ -126,6 +126,8 @@ print("ok")
         extra = {"CORTO_DELTA": "cta"}
     elif mode == "deltaseq":                      # ... with every round on its sequential-warp path
         extra = {"CORTO_DELTA": "seq"}
+    elif mode == "unpackchain":                   # one CTA per unpack chain (the default only for batches with >= 2 x SMs chains)
+        extra = {"CORTO_UNPACK": "chain"}
     elif mode.startswith("overlap"):
         extra = {"CORTO_OVERLAP": mode[-1]}
     elif mode.startswith("adjagg"):
