@@ -1814,9 +1814,12 @@ int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, co
 	static int mode = -1;
 	if(mode < 0) { const char *e = getenv("CORTO_UNPACK"); mode = (e && e[0] == 'c') ? 1 : ((e && e[0] == 'l') ? 2 : 0); }
 	const bool chain = mode == 1 || (mode == 0 && nchains >= 2u*(uint32_t)sms);
-	static int occ = -1;                  // CORTO_UNPACK_OCC=6: cap registers at 40 for 6 CTAs per SM (a few spills) instead of 5
-	if(occ < 0) { const char *e = getenv("CORTO_UNPACK_OCC"); occ = (e && e[0] == '6') ? 6 : 5; }
-	if(chain && occ == 6) k_unpack_chain<6><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+	// 5 CTAs per SM at 48 registers; capping at 40 (a few spills) makes it 6, which pays exactly when it lets every chain be
+	// resident at once (configs[1]: 768 chains, 740 vs 888 slots: 1.02 -> 0.89 ms) and costs otherwise (configs[3]: 2.57 -> 2.78 ms)
+	static int occ = -1;                  // CORTO_UNPACK_OCC=5|6 forces either
+	if(occ < 0) { const char *e = getenv("CORTO_UNPACK_OCC"); occ = (e && (e[0] == '5' || e[0] == '6')) ? e[0] - '0' : 0; }
+	const bool six = occ == 6 || (occ == 0 && nchains > 5u*(uint32_t)sms && nchains <= 6u*(uint32_t)sms);
+	if(chain && six) k_unpack_chain<6><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
 	else if(chain) k_unpack_chain<5><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
 	else k_unpack_fused<true><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
