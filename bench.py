@@ -229,7 +229,7 @@ def main():
     if dom:
         ach = (in_bytes + out_bytes) / (stage_ms[dom] * 1e-3) / 1e9
         kernel_of = {"clers": "k_clers_lf", "delta": "k_delta_mesh", "cloud_fused": "k_unpack_fused<CLOUD>", "tun_decode": "k_tun_decode",
-                     "bit_unpack": "k_unpack_fused<MESH>", "normals": "k_adj_build + k_normal_estimate", "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
+                     "bit_unpack": "k_unpack_chain / k_unpack_fused<MESH>", "normals": "k_adj_build + k_normal_estimate", "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/): measured per mesh on a 16-mesh
         # batch of this workload, scaled to this batch; null where no capture exists for the kernel/workload pair
         traffic = None
