@@ -12,8 +12,14 @@ data-path collective; torch.distributed is used only for the barri
   e2e       same metric through the public API with HOST buffers: H2D of the blobs from pinned memory, kernels,
             D2H of every output arena into pinned memory, all inside the timed region.
   roofline  dominant kernel (by measured device time): algorithmic bytes (blob + bound outputs) / its mean
-            duration (CUDA events on the launch stream, inside the timed region) against MEASURED_PEAKS.json hbm_gbs.
+            duration (the library's CUDA-event stage timers over a re-run of the same steps right after the timed region)
+            against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores, rank 0, N=1 only.
+
+Inputs: the synthetic meshes are ENCODED by the reference's own Encoder (oracle/workloads.py -> oracle/_ref; this repo has no
+encoder, SURVEY §8 puts it out of scope) as set-up before anything is timed; without oracle/_ref one pre-encoded blob per
+workload from tests/golden/bench/ is replicated and `data` says so.  Nothing under oracle/ runs inside a timed region of the
+default arm except the cpu_baseline leg; the decode itself goes through corto_b200 (C ABI) only.
 
 `--impl reference` times the reference's own single-threaded C++ decoder, one Decoder per host thread over all host
 threads, on the same workload (bounded sample per step).
