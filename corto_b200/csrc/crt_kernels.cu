@@ -1,22 +1,25 @@
 // crt_kernels.cu — hand-written sm_100a kernels of the corto decode path (no tensor cores: there is no dense
 // contraction anywhere in this path, it is byte / bit / index work bound by HBM and by one serial automaton).
 //
-// Kernel      replaces (reference file:line)                                      parallel structure
-// k_tun_tables   Tunstall::createDecodingTables2   src/tunstall.cpp:125-256       one warp per entropy block
-// k_tun_decode   Tunstall::decompress              src/tunstall.cpp:430-452       tiles of compressed bytes; the
-//                + InStream::decompress NONE path  src/cstream.cpp:68-73          dictionary staged in smem by TMA
-//                                                                                 (cp.async.bulk + mbarrier); output
-//                                                                                 offset = decoupled look-back scan
-// k_unpack_fused decodeArray / decodeValues        include/corto/cstream.h:294-360 tiles of 1024 vertices, all components;
-//                (+ cloud delta + dequantise for point clouds)                    bit offset / running sum = look-back scans
-// k_clers        Decoder::decodeFaces              src/decoder.cpp:204-358        serial automaton, one warp / mesh
-// k_delta_mesh   GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp / (mesh, attr), lane / comp
-//                NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
-// k_cloud_fused  point clouds: unpack + running delta (vertex_attribute.h:177-181, normal_attribute.cpp:202-207) + dequantise
+// Kernel           replaces (reference file:line)                                   parallel structure
+// k_tun_tables     Tunstall::createDecodingTables2   src/tunstall.cpp:125-256       one warp per entropy block
+// k_tun_decode     Tunstall::decompress              src/tunstall.cpp:430-452       tiles of compressed bytes; the dictionary
+//                  + InStream::decompress NONE path  src/cstream.cpp:68-73          staged in smem by TMA (cp.async.bulk +
+//                                                                                   mbarrier); offsets = decoupled look-back
+// k_unpack_chain   decodeArray / decodeValues        include/corto/cstream.h:294-360  meshes: tiles of 1024 vertices, all
+// k_unpack_fused<MESH>                                                               components; bit offset = running total
+//                                                                                   per chain, or block scan + look-back
+// k_unpack_fused<CLOUD>  ... + GenericAttr::deltaDecode (cloud) vertex_attribute.h:177-181, NormalAttr::deltaDecode (cloud)
+//                  normal_attribute.cpp:202-207 + dequantize: point clouds in ONE pass
+// k_clers_lf       Decoder::decodeFaces              src/decoder.cpp:204-358        serial automaton, two warps per mesh
+// k_clers          (the same, single-warp variant kept as A/B baseline, CORTO_CLERS=1)
+// k_delta_mesh     GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp per (mesh, attribute[, component])
+//                  NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
+// k_delta_mesh_cta (the same, one CTA per chain, 256 vertices per round; experiment switch CORTO_DELTA=cta)
 // k_adj_build / k_scan_u32 / k_normal_estimate
-//                markBoundary, estimateNormals, computeNormals   normal_attribute.cpp:24-59, 281-325
-// k_dequant      GenericAttr::dequantize, NormalAttr::dequantize, ColorAttr::dequantize
-//                vertex_attribute.h:184-230, normal_attribute.cpp:257-279, color_attribute.cpp:76-95
+//                  markBoundary, estimateNormals, computeNormals   normal_attribute.cpp:24-59, 281-325
+// k_dequant        GenericAttr::dequantize, NormalAttr::dequantize, ColorAttr::dequantize
+//                  vertex_attribute.h:184-230, normal_attribute.cpp:257-279, color_attribute.cpp:76-95
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
