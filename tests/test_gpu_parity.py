@@ -84,6 +84,32 @@ def test_batch_mixed():
                 _same("batch2[%d]/%s" % (i, k), got[k], w)
 
 
+def test_batch_baseline_sizes():
+    """BASELINE configs[1] / configs[2] at their real mesh sizes in one batch large enough for the big-batch code paths bench.py
+    times (one CTA per unpack chain at 6 CTAs per SM, one warp per (mesh, attribute) in the delta inverse): 2 distinct 128 K-vertex
+    meshes x 128 (= the 256 meshes of configs[1]) and 2 distinct 167 K-point clouds x 16, every copy compared with the oracle's
+    decode of its blob."""
+    if not refshim.available():
+        pytest.skip("needs the reference shim to encode")
+    import torch
+    from oracle import workloads
+    distinct = [workloads._c2(1), workloads._c2(2), workloads._c3(1), workloads._c3(2)]
+    want = [pyoracle.decode(b, color_out=4) for b in distinct]
+    order = ([0, 1] * 128) + ([2, 3] * 16)
+    bd = corto_b200.BatchDecoder([distinct[k] for k in order], color_components=4)
+    bd.allocate(fill=0xA5)
+    bd.upload()
+    bd.decode()
+    torch.cuda.synchronize()
+    rc, st = bd.status()
+    assert rc == 0, st
+    for i, k in enumerate(order):
+        got = bd.mesh_outputs(i)
+        for name, w in want[k].items():
+            if isinstance(w, np.ndarray):
+                _same("baseline[%d]/%s" % (i, name), got[name], w)
+
+
 def test_tarta():
     import os
     if not os.path.exists(refshim.TARTA):
