@@ -105,6 +105,49 @@ def test_truncated_blobs_are_rejected_not_read_out_of_bounds(name):
     L.crt_batch_destroy(h)
 
 
+@pytest.mark.parametrize("name", ["grid_est", "cloud_all", "groups4_border", "torus"])
+def test_mutated_directories_never_escape_the_blob(name):
+    """Random byte edits in the header / block headers (sizes, counts, string lengths, nsym ...) through the C ABI: the host walk
+    either rejects the blob or builds a batch that answers its queries; the product library must survive all of it (the
+    sanitizer run below checks the same walk for out-of-bounds reads byte by byte)."""
+    blob = _golden(name)
+    L = corto_b200.lib()
+    rs = np.random.RandomState(1234)
+    n = len(blob)
+    accepted = 0
+    for trial in range(1500):
+        bad = refshim.aligned_blob(blob.tobytes())
+        # most edits land in the first 256 bytes (header, group table, first block headers), the rest anywhere
+        for _ in range(int(rs.randint(1, 4))):
+            pos = int(rs.randint(0, min(n, 256))) if rs.uniform() < 0.7 else int(rs.randint(0, n))
+            bad[pos] = rs.randint(0, 256) if rs.uniform() < 0.5 else (0xFF if rs.uniform() < 0.5 else 0x00)
+        ptrs = (C.c_void_p * 1)(bad.ctypes.data)
+        lens = (C.c_int * 1)(n)
+        h = L.crt_batch_create(1, ptrs, lens)
+        if h:
+            accepted += 1
+            nv, nf = C.c_uint32(), C.c_uint32()
+            mask = C.c_uint32()
+            assert L.crt_batch_mesh_info(h, 0, C.byref(nv), C.byref(nf), C.byref(mask)) == 0
+            assert L.crt_batch_total_bytes(h) == n
+            L.crt_batch_destroy(h)
+    assert accepted > 0            # payload-only edits must still parse (the walk reads no payload byte)
+
+
+def test_walk_under_sanitizers(tmp_path):
+    """crt_walk.cpp under AddressSanitizer + UBSan: every truncation and 3000 random edits per fixture, each in a heap buffer of
+    exactly the blob's size (tests/host_emul/walk_fuzz.cpp).  Any out-of-bounds read aborts the run."""
+    exe = str(tmp_path / "walk_fuzz")
+    src = [os.path.join(ROOT, "tests", "host_emul", "walk_fuzz.cpp"), os.path.join(ROOT, "corto_b200", "csrc", "crt_walk.cpp")]
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", os.path.join(ROOT, "include"),
+                        "-o", exe] + src, capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not available here: " + r.stderr[-200:])
+    for name in ("grid_est", "cloud_all", "groups4_border", "torus", "none_entropy", "const_color", "radius_both"):
+        p = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", name + ".crt"), "3000"], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0 and "accepted" in p.stdout, (name, p.stdout[-300:], p.stderr[-2000:])
+
+
 def test_batch_layout_without_gpu():
     blobs = [_golden(n) for n in ("grid_est", "cloud_all", "torus", "triangle")]
     bd_ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
