@@ -1,0 +1,354 @@
+// crt_clers_cta.cu — k_clers_cta: Decoder::decodeFaces (src/decoder.cpp:204-358) with ONE CTA of 256 threads per mesh.
+//
+// The automaton is serial per mesh, but a run of VERTEX / LEFT symbols — 99.5 % of a regular mesh, strips of hundreds of
+// symbols — is a closed form of two prefix counts (crt_device.cuh, "v7"): thread = symbol, 256 symbols per step, two barriers
+// per step, links and labels in the same pass.  Everything else runs on thread 0 through the scalar machine clers_merged.
+//
+//   shared memory (dynamic):  labels  uint4[R]   (v0, v1, v2, -) of every materialised front edge, ring over edge ids
+//                             links   uint2[R]   (prev, next)
+//                             flags   u8[R]      0 queued+alive | CLERS_DEL | CLERS_NQ (implicit FIFO: pop = scan for a 0 byte)
+//                             symbols u8[4][1024] ring of the CLERS stream, filled by TMA 1-D bulk copies (cp.async.bulk +
+//                                                mbarrier) three segments ahead of the cursor, so no step waits on global memory
+//   global memory:            reach-back store for ring entries older than the window (ClersScratch slot), delayed stack,
+//                             faces and predictions (written directly, one face / one prediction per thread).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "crt_device.cuh"
+#include "crt_kernels.h"
+#include "crt_ptx.cuh"
+
+namespace crtb {
+
+extern __shared__ __align__(16) uint8_t cta_smem[];
+
+constexpr int CT = 256;                     // threads per CTA = symbols per window step
+constexpr int CTW = CT/32;
+constexpr uint32_t CTA_SEG = 1024;          // bytes per symbol segment
+constexpr uint32_t CTA_NSEG = 4;            // segments in the ring
+constexpr int CTA_SCALAR_BUDGET = 48;       // symbols per scalar chunk (each creates at most 3 ids)
+
+struct CtaRings {
+	uint32_t aA, aB, aX, aS;     // shared-space byte addresses
+	uint32_t RM, sq;             // ring mask; sequence number of this mesh's segment 0 (slot = (sq + seg) & 3)
+	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const {
+		[[maybe_unused]] uint32_t d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & RM) << 4)));
+	}
+	__device__ __forceinline__ uint32_t ldA0(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aA + ((id & RM) << 4))); return v; }
+	__device__ __forceinline__ void stA(uint32_t id, uint32_t a, uint32_t b, uint32_t c) {
+		asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(aA + ((id & RM) << 4)), "r"(a), "r"(b), "r"(c), "r"(0u) : "memory");
+	}
+	__device__ __forceinline__ void ldB(uint32_t id, uint32_t &p, uint32_t &n) const {
+		asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(p), "=r"(n) : "r"(aB + ((id & RM) << 3)));
+	}
+	__device__ __forceinline__ void stB(uint32_t id, uint32_t p, uint32_t n) {
+		asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(aB + ((id & RM) << 3)), "r"(p), "r"(n) : "memory");
+	}
+	__device__ __forceinline__ void stB_prev(uint32_t id, uint32_t p) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3)), "r"(p) : "memory"); }
+	__device__ __forceinline__ void stB_next(uint32_t id, uint32_t n) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3) + 4u), "r"(n) : "memory"); }
+	__device__ __forceinline__ uint32_t ldFl(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aX + (id & RM))); return v; }
+	__device__ __forceinline__ void stFl(uint32_t id, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(aX + (id & RM)), "r"(v) : "memory"); }
+	__device__ __forceinline__ uint32_t sym(uint32_t i) const {
+		uint32_t v;
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aS + (((sq + (i >> 10)) & (CTA_NSEG - 1u)) << 10) + (i & (CTA_SEG - 1u))));
+		return v;
+	}
+};
+
+struct CtaShared {
+	MergedState S;
+	int32_t mode;                 // next step: 0 scalar chunk, 3 window, 4 pop, 1 done, < 0 error
+	uint32_t tried;               // the last window attempt bailed: one symbol goes the scalar way
+	uint32_t flag, newprev;
+	uint32_t wV[2][CTW], wL[2][CTW];
+	uint32_t aL[CT + 1];
+	uint32_t chain[CT + 1];
+	uint32_t work;
+	alignas(8) uint64_t bar[CTA_NSEG];
+};
+
+// ---- symbol segments -----------------------------------------------------------------------------------------------------
+// Segment s of the current mesh (symbols [1024 s, 1024 s + 1024)) is copy number sq + s of this CTA: slot (sq + s) & 3, and
+// the ((sq + s) >> 2)-th use of that slot's mbarrier.  Segments up to (cler >> 10) + 3 are in flight (the slot of segment s + 4
+// is free once the cursor has left segment s).  `issued` / `ready` are uniform counters every thread keeps in registers.
+__device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &rg, CtaShared &sh, uint32_t cler, uint32_t nseg, uint32_t &issued, uint32_t &ready,
+                                            uint32_t upto /* symbols below this index must be readable */) {
+	const uint32_t want = min(nseg, (cler >> 10) + CTA_NSEG);
+	if(issued < want) {
+		if(threadIdx.x == 0) {
+			fence_proxy_async();
+			for(uint32_t s = issued; s < want; s++) {
+				const uint32_t q = rg.sq + s, slot = q & (CTA_NSEG - 1u);
+				uint32_t bytes = io.nclers - s*CTA_SEG;
+				if(bytes > CTA_SEG) bytes = CTA_SEG;
+				bytes = (bytes + 15u) & ~15u;                      // the symbol arena pads every block (crt_api.cu: add_block)
+				mbar_expect_tx(&sh.bar[slot], bytes);
+				tma_bulk_g2s(cta_smem + (rg.aS - smem_u32(cta_smem)) + slot*CTA_SEG, io.clers + (size_t)s*CTA_SEG, bytes, &sh.bar[slot]);
+			}
+		}
+		issued = want;
+	}
+	uint32_t need = (upto + CTA_SEG - 1u) >> 10;
+	if(need > issued) need = issued;
+	while(ready < need) {
+		const uint32_t q = rg.sq + ready;
+		mbar_wait(&sh.bar[q & (CTA_NSEG - 1u)], (q >> 2) & 1u);
+		ready++;
+	}
+}
+
+// ---- CTA-wide window over a run of VERTEX / LEFT symbols -------------------------------------------------------------------
+// Runs window after window while the run lasts.  All decisions are taken on values every thread reads from shared memory, so
+// every branch around a barrier is uniform.
+__device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready) {
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+	const uint32_t below = (1u << lane) - 1u;
+	uint32_t cler = sh.S.cler, start = sh.S.start;
+	const uint32_t end = sh.S.end;
+	uint32_t done = 0, it = 0;
+	bool bail = false;
+	for(;; it ^= 1u) {
+		const uint32_t lim = min((uint32_t)CT, min(io.nclers - cler, end - start));
+		cta_symbols(io, rg, sh, cler, nseg, issued, ready, cler + lim);
+		// ---- phase A: classify my symbol
+		const uint32_t c = tid < lim ? rg.sym(cler + tid) : 0xffu;
+		const bool isV = c == C_VERTEX, isL = c == C_LEFT;
+		const uint32_t bV = __ballot_sync(FULL, isV), bL = __ballot_sync(FULL, isL);
+		if(lane == 0) { sh.wV[it][w] = bV; sh.wL[it][w] = bL; }
+		__syncthreads();                                   // B1 (also: state and rings written by the previous step are visible)
+		// ---- phase B: ranks
+		const uint32_t prev = sh.S.prev, next = sh.S.next, nfront = sh.S.nfront, vcount = sh.S.vcount, eflush = sh.S.eflush;
+		const uint32_t s_v0 = sh.S.v0, s_v1 = sh.S.v1, s_v2 = sh.S.v2;
+		uint32_t m = CT, nVb = 0, nLb = 0, nV = 0, nL = 0;
+		bool prevIsV = false;
+#pragma unroll
+		for(int j = 0; j < CTW; j++) {
+			uint32_t v = sh.wV[it][j], l = sh.wL[it][j];
+			if(m == CT) {
+				const uint32_t stop = ~(v | l);
+				if(stop) {
+					const uint32_t k = (uint32_t)__ffs(stop) - 1u;
+					m = (uint32_t)j*32u + k;
+					const uint32_t pm = (1u << k) - 1u;
+					v &= pm; l &= pm;
+				}
+			} else { v = 0; l = 0; }
+			nV += __popc(v); nL += __popc(l);
+			if((uint32_t)j < w) { nVb += __popc(v); nLb += __popc(l); }
+			else if((uint32_t)j == w) { nVb += __popc(v & below); nLb += __popc(l & below); if(lane) prevIsV = (v >> (lane - 1u)) & 1u; }
+			if((uint32_t)j + 1u == w && lane == 0) prevIsV = (v >> 31) & 1u;
+		}
+		if(m > lim) m = lim;                               // (lanes past lim read 0xff: m <= lim already; belt and braces)
+		const bool mine = tid < m;
+		if(m < 2u || nfront + nV > io.cap || vcount + nV > io.nvert || nfront + nV > eflush + R) { bail = done == 0; break; }
+		// ---- prev chain, fast path: consecutive ids prev, prev + 1, ... (the queued edges of one earlier strip)
+		uint32_t id = prev + nLb, a = 0;
+		bool good = true;
+		if(mine && isL) {
+			good = id >= eflush && id < nfront && id != next;
+			if(good) {
+				uint32_t pk, pn;
+				rg.ldB(id, pk, pn);
+				a = rg.ldA0(id);
+				if(nLb + 1u == nL) sh.newprev = pk; else good = pk == id + 1u;
+				sh.aL[nLb] = a;
+			}
+		}
+		if(nL == 0 && tid == 0) sh.newprev = prev;
+		if(!__syncthreads_and(good)) {                     // B2
+			// slow path: thread 0 walks the chain; a walk that wraps around to the right-hand neighbour (small loop) means the
+			// links change inside this window: scalar machine
+			if(tid == 0) {
+				uint32_t q = prev, ok = 1;
+				for(uint32_t k = 0; k < nL; k++) {
+					sh.chain[k] = q;
+					if(q == next || q >= nfront) { ok = 0; break; }
+					uint32_t pp, pq;
+					if(q >= eflush) rg.ldB(q, pp, pq); else { const uint2_t t_ = lead_g_load(io.eb, q); pp = t_.x; pq = t_.y; }
+					(void)pq;
+					q = pp;
+				}
+				sh.newprev = q;
+				sh.flag = ok;
+			}
+			__syncthreads();
+			if(!sh.flag) { bail = done == 0; break; }
+			if(mine && isL) {
+				id = sh.chain[nLb];
+				if(id >= eflush) a = rg.ldA0(id); else a = follow_g_load(io.ea, id).x;
+				sh.aL[nLb] = a;
+			}
+			__syncthreads();
+		}
+		// ---- phase C: labels, outputs, ring records
+		if(mine) {
+			const uint32_t v0i = nLb ? sh.aL[nLb - 1u] : s_v0;
+			const uint32_t v1i = nVb ? vcount + nVb - 1u : s_v1;
+			uint32_t v2i;
+			if(tid == 0) v2i = s_v2;
+			else if(prevIsV) v2i = nVb > 1u ? vcount + nVb - 2u : s_v1;
+			else v2i = nLb > 1u ? sh.aL[nLb - 2u] : s_v0;
+			const uint32_t x = vcount + nVb;
+			const uint32_t third = isV ? x : a;
+			const size_t at = (size_t)(start + tid)*3u;
+			if(io.faces16) { io.faces16[at] = (uint16_t)v1i; io.faces16[at + 1] = (uint16_t)v0i; io.faces16[at + 2] = (uint16_t)third; }
+			else { io.faces32[at] = v1i; io.faces32[at + 1] = v0i; io.faces32[at + 2] = third; }
+			if(isV) {
+				((uint4 *)io.pred)[x] = make_uint4(v1i, v0i, v2i, 0u);
+				const uint32_t b = nfront + nVb;
+				rg.stA(b, x, v1i, v0i);
+				rg.stB(b, nVb + 1u < nV ? b + 1u : CLERS_NOLINK, nVb ? b - 1u : next);
+				rg.stFl(b, 0u);
+			} else {
+				if(id >= eflush) rg.stFl(id, CLERS_DEL); else lead_g_set_flag(io.fl, id, CLERS_DEL);
+			}
+			if(tid == m - 1u) { sh.S.v0 = isL ? a : v0i; sh.S.v1 = isV ? x : v1i; sh.S.v2 = isV ? v1i : v0i; }
+		}
+		if(tid == 0) {
+			if(nV) {
+				if(next >= eflush) rg.stB_prev(next, nfront); else clers_g_set_prev(io.eb, next, nfront);
+				sh.S.next = nfront + nV - 1u;
+			}
+			sh.S.nfront = nfront + nV; sh.S.vcount = vcount + nV;
+			sh.S.prev = sh.newprev;
+			sh.S.start = start + m; sh.S.cler = cler + m;
+			sh.S.lp = sh.S.ln = 1; sh.S.cf = CLERS_NOID;
+			sh.S.have = start + m < end ? 1u : 0u;
+		}
+		cler += m; start += m; done += m;
+		if(m < (uint32_t)CT || start >= end || cler >= io.nclers) break;      // the run ended (or the group / the stream did)
+		if(nfront + nV + (uint32_t)CT > eflush + R) break;                     // ring entries have to be written back first
+	}
+	if(tid == 0) { sh.mode = 0; sh.tried = bail ? 1u : 0u; }
+}
+
+// ---- CTA-wide pop of the implicit FIFO: 256 flag bytes per step -------------------------------------------------------------
+__device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh) {
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+	uint32_t scan = sh.S.scan;
+	const uint32_t nfront = sh.S.nfront, eflush = sh.S.eflush;
+	uint32_t found = CLERS_NOID, it = 0;
+	while(scan < nfront) {
+		const uint32_t id = scan + tid;
+		uint32_t fl = 0xffu;
+		if(id < nfront) fl = id >= eflush ? rg.ldFl(id) : lead_g_flag(io.fl, id);
+		const uint32_t alive = __ballot_sync(FULL, fl == 0u);
+		if(lane == 0) sh.wV[it][w] = alive;
+		__syncthreads();
+#pragma unroll
+		for(int j = CTW - 1; j >= 0; j--) { const uint32_t x = sh.wV[it][j]; if(x) found = scan + (uint32_t)j*32u + (uint32_t)__ffs(x) - 1u; }
+		if(found != CLERS_NOID) { scan = found + 1u; break; }
+		scan += CT;
+		it ^= 1u;
+	}
+	if(tid == 0) {
+		sh.S.scan = scan < nfront ? scan : nfront;
+		if(found != CLERS_NOID) {
+			uint32_t p, q, a, b, c;
+			if(found >= eflush) { rg.ldB(found, p, q); rg.ldA(found, a, b, c); }
+			else { const uint2_t t_ = lead_g_load(io.eb, found); p = t_.x; q = t_.y; const uint4_t u_ = follow_g_load(io.ea, found); a = u_.x; b = u_.y; c = u_.z; }
+			sh.S.prev = p; sh.S.next = q; sh.S.v0 = a; sh.S.v1 = b; sh.S.v2 = c;
+			sh.S.lp = sh.S.ln = 0; sh.S.have = 1; sh.S.cf = found;
+		}
+		sh.mode = 0; sh.tried = 0;
+	}
+}
+
+__global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket, uint32_t R,
+                                                  uint32_t runmin) {
+	__shared__ CtaShared sh;
+	const uint32_t tid = threadIdx.x;
+	CtaRings rg;
+	{
+		uint32_t sbase;
+		asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(cta_smem)));
+		rg.aA = sbase; rg.aB = sbase + R*16u; rg.aX = rg.aB + R*8u; rg.aS = rg.aX + R;
+		rg.RM = R - 1u; rg.sq = 0;
+	}
+	if(tid == 0) for(uint32_t k = 0; k < CTA_NSEG; k++) mbar_init(&sh.bar[k], 1);
+	const uint32_t KEEP = R - 2u*(uint32_t)CT;             // ring entries kept after a write-back
+	for(;;) {
+		__syncthreads();
+		if(tid == 0) sh.work = atomicAdd(ticket, 1u);
+		__syncthreads();
+		const uint32_t wk = sh.work;
+		if(wk >= nwork) break;
+		const uint32_t mi = mesh_order[wk];
+		const MeshDesc *M = B.mesh + mi;
+		const TunDesc td = B.tun[M->clers_tun];
+		ClersIO io;
+		io.clers = B.symbols + td.out_off; io.nclers = td.size;
+		io.split = (const uint32_t *)(B.blobs + M->split_off); io.split_nwords = M->split_nwords;
+		io.group_ends = B.group_ends + M->group0; io.ngroups = M->ngroups;
+		io.nvert = M->nvert; io.nface = M->nface;
+		const size_t slot = blockIdx.x;
+		io.cap = scratch.cap;
+		io.ea = scratch.ea + slot*scratch.cap; io.eb = scratch.eb + slot*scratch.cap;
+		io.order = scratch.order + slot*scratch.cap; io.delayed = scratch.delayed + slot*scratch.cap;
+		const uint32_t need = 3u*M->max_group_faces + 3u;
+		if(need < io.cap) io.cap = need;
+		io.faces32 = M->index16 ? nullptr : (uint32_t *)M->face_ptr;
+		io.faces16 = M->index16 ? (uint16_t *)M->face_ptr : nullptr;
+		io.pred = (uint32_t *)M->pred_ptr;
+		io.fl = (uint8_t *)io.order;                       // no FIFO is stored: the `order` scratch backs the flag ring
+		const int splitbits = ilog2_u32(io.nvert) + 1;
+		const uint32_t nseg = (io.nclers + CTA_SEG - 1u)/CTA_SEG;
+		uint32_t issued = 0, ready = 0;
+		if(tid == 0) { merged_init(sh.S); sh.mode = 0; sh.tried = 0; }
+		int mode;
+		for(;;) {
+			__syncthreads();                               // state, rings and outputs of the previous step are visible
+			mode = sh.mode;
+			if(mode == 1 || mode < 0) break;
+			const uint32_t cler = sh.S.cler, nfront = sh.S.nfront, eflush = sh.S.eflush;
+			if(nfront + (uint32_t)CT > eflush + R) {       // write ring entries leaving the window back to the reach-back store
+				const uint32_t e1 = nfront - KEEP;
+				for(uint32_t id = eflush + tid; id < e1; id += CT) {
+					uint32_t a, b, c, p, n;
+					rg.ldA(id, a, b, c); rg.ldB(id, p, n);
+					io.ea[id] = EdgeA{a, b, c, 0}; io.eb[id] = EdgeB{p, n}; io.fl[id] = (uint8_t)rg.ldFl(id);
+				}
+				__syncthreads();
+				if(tid == 0) sh.S.eflush = e1;
+				continue;
+			}
+			cta_symbols(io, rg, sh, cler, nseg, issued, ready, min(io.nclers, cler + (uint32_t)CT + 64u));
+			if(mode == 3) cta_window(io, rg, sh, R, nseg, issued, ready);
+			else if(mode == 4) cta_pop(io, rg, sh);
+			else if(tid == 0) {
+				const bool tried = sh.tried != 0;
+				int rc = clers_merged(io, rg, sh.S, tried ? 1 : CTA_SCALAR_BUDGET, !tried, runmin, splitbits);
+				sh.tried = 0;
+				sh.mode = rc;
+			}
+		}
+		// every copy that was issued has to land before the slots are reused by the next mesh
+		while(ready < issued) { const uint32_t q = rg.sq + ready; mbar_wait(&sh.bar[q & (CTA_NSEG - 1u)], (q >> 2) & 1u); ready++; }
+		rg.sq += issued;
+		uint32_t vcount = sh.S.vcount;
+		const bool bad = mode < 0;
+		if(tid == 0) { if(bad) B.status[mi] = -5; B.vertex_count[mi] = vcount; }
+		// vertices the stream never created (corrupt / truncated input): neutral prediction so later passes stay in bounds
+		uint4 *pred = (uint4 *)M->pred_ptr;
+		if(bad) vcount = 0;
+		for(uint32_t v = vcount + tid; v < M->nvert; v += CT) pred[v] = make_uint4(0, 0, 0, 0);
+	}
+}
+
+int launch_clers_cta(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, uint32_t runmin, cudaStream_t s) {
+	// ring size: as much shared memory per mesh as leaves every mesh of the batch resident (up to 8 CTAs of 256 threads per SM)
+	uint32_t R = 8192;
+	if(nwork > (uint32_t)sms) R = 4096;
+	if(nwork > 2u*(uint32_t)sms) R = 2048;
+	const size_t smem = (size_t)R*25u + CTA_NSEG*CTA_SEG;
+	cudaError_t e = cudaFuncSetAttribute(k_clers_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if(e != cudaSuccess) return (int)e;
+	const uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
+	k_clers_cta<<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R, runmin);
+	e = cudaGetLastError();
+	return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace crtb

@@ -896,6 +896,197 @@ template <class RG> CRT_HD int clers_follow(const ClersIO &io, RG &rg, FollowSta
 	return rc;
 }
 
+// ---- CLERS automaton, v7: ONE merged machine per mesh, run by a whole CTA (k_clers_cta) -----------------------------------
+// v4-v6 split links and labels over two warps to shorten the serial chain; what bounds them is still one warp stepping
+// through 32 symbols at a time (~40 dependent collectives per window).  v7 turns the closed form of a VERTEX/LEFT run into a
+// CTA-wide scan: 256 threads take 256 symbols per step, thread = symbol, two barriers per step, links AND labels in the same
+// pass (so there is no log and no second machine):
+//   V at rank r among the V's:  new vertex x = vcount + r, new queued edge b = nfront + r with links (b+1 | deferred, b-1 | next)
+//   L at rank k among the L's:  consumes chain[k], the k-th edge of the prev chain (prev, prev.prev, ...) — usually the
+//                               consecutive ids prev, prev+1, ... of ONE earlier strip, checked with one load per L
+//   labels: v1 = last vertex created before me, v0 = label of the edge the last L before me consumed, v2 = v1 / v0 of the symbol
+//           before me — all functions of the two ranks.
+// Everything else (BOUNDARY, DELAY, RIGHT, END, SPLIT, start triangles, runs shorter than the threshold) goes through the scalar
+// machine below on thread 0, which shares the rings (labels 16 B + links 8 B + flag byte per materialised edge, implicit
+// FIFO = scan of the flag bytes, 256 per step by the whole CTA).  Faces and predictions go straight to global memory.
+struct MergedState {
+	uint32_t cler, vcount;
+	uint64_t splitpos;
+	uint32_t g, start, end;            // current group; face cursor / end of group, in FACES
+	uint32_t nfront, scan, ndel;       // ids allocated; next id the implicit FIFO looks at; delayed-stack depth
+	uint32_t have, lp, ln, cf;         // current edge valid; deferred incoming links; its id (CLERS_NOID while it has no record)
+	uint32_t v0, v1, v2, prev, next;   // current edge
+	uint32_t eflush;                   // ids below live in the global backing store
+	uint32_t bad;
+};
+CRT_HD void merged_init(MergedState &S) {
+	S.cler = S.vcount = 0; S.splitpos = 0; S.g = S.start = S.end = 0; S.nfront = S.scan = S.ndel = 0;
+	S.have = S.lp = S.ln = 0; S.cf = CLERS_NOID; S.v0 = S.v1 = S.v2 = S.prev = S.next = 0; S.eflush = 0; S.bad = 0;
+}
+CRT_COLD static void merged_g_storeA(EdgeA *ea, uint32_t x, uint32_t a, uint32_t b, uint32_t c) { ea[x] = EdgeA{a, b, c, 0}; }
+CRT_COLD static void merged_g_storeB(EdgeB *eb, uint32_t x, uint32_t p, uint32_t n) { eb[x] = EdgeB{p, n}; }
+
+// Scalar machine.  RG: ldA/stA (labels), ldB/stB/stB_prev/stB_next (links), ldFl/stFl (flags), sym(i) (symbol i of the stream;
+// valid for i < nclers).  Consumes at most `budget` symbols.  Returns 1 when all groups are done, 0 to be called again (budget),
+// 3 (only with vec) when at least `runmin` VERTEX/LEFT symbols lie ahead of a valid current edge (caller: CTA-wide window),
+// 4 (only with vec) when the implicit FIFO has to be scanned (caller: CTA-wide pop), < 0 on a topology error.
+// Errors set a sticky flag and indices are clamped (nothing is written out of bounds); the flag is reported when the chunk ends.
+template <class RG> CRT_HD int clers_merged(const ClersIO &io, RG &rg, MergedState &S, int budget, bool vec, uint32_t runmin, int splitbits) {
+	uint32_t cler = S.cler, vcount = S.vcount, start = S.start, end = S.end, g = S.g;
+	uint32_t nfront = S.nfront, scan = S.scan, ndel = S.ndel, bad = S.bad;
+	uint64_t splitpos = S.splitpos;
+	uint32_t have = S.have, lp = S.lp, ln = S.ln, f = S.cf, v0 = S.v0, v1 = S.v1, v2 = S.v2, prev = S.prev, next = S.next;
+	uint32_t eflush = S.eflush;
+	const uint32_t nclers = io.nclers, nvert = io.nvert, cap = io.cap;
+	uint32_t n = nclers - cler;
+	if(n > (uint32_t)budget) n = (uint32_t)budget;
+	int rc = 0;
+#define MG_SET_NEXT(x, v) do { if((x) >= eflush) rg.stB_next(x, v); else clers_g_set_next(io.eb, x, v); } while(0)
+#define MG_SET_PREV(x, v) do { if((x) >= eflush) rg.stB_prev(x, v); else clers_g_set_prev(io.eb, x, v); } while(0)
+#define MG_LOADB(ID_, P_, Q_) do { if((ID_) >= eflush) rg.ldB(ID_, P_, Q_); else { const uint2_t t_ = lead_g_load(io.eb, ID_); P_ = t_.x; Q_ = t_.y; } } while(0)
+#define MG_LOADA(ID_, A_, B_, C_) do { if((ID_) >= eflush) rg.ldA(ID_, A_, B_, C_); else { const uint4_t t_ = follow_g_load(io.ea, ID_); A_ = t_.x; B_ = t_.y; C_ = t_.z; } } while(0)
+#define MG_FLAG(ID_) (((ID_) >= eflush) ? rg.ldFl(ID_) : lead_g_flag(io.fl, ID_))
+#define MG_SET_FLAG(ID_, V_) do { if((ID_) >= eflush) rg.stFl(ID_, V_); else lead_g_set_flag(io.fl, ID_, V_); } while(0)
+#define MG_NEWID(ID_) do { ID_ = nfront; bad |= (nfront >= cap); nfront += (nfront < cap); } while(0)
+#define MG_MATERIALISE()                                                                                 \
+	do {                                                                                                 \
+		MG_NEWID(f);                                                                                     \
+		rg.stB(f, prev, next); rg.stA(f, v0, v1, v2); rg.stFl(f, CLERS_NQ);                              \
+		if(lp) MG_SET_NEXT(prev, f);                                                                     \
+		if(ln) MG_SET_PREV(next, f);                                                                     \
+		lp = ln = 0;                                                                                     \
+	} while(0)
+#define MG_FACE(A_, B_, C_) do { if(start < io.nface) clers_put_face(io, (size_t)start*3u, A_, B_, C_); else bad = 1; start++; } while(0)
+	for(;;) {
+		if(!have) {
+			if(start >= end) {                         // next group: fresh front (decoder.cpp:173-178, 207-221)
+				if(g >= io.ngroups) { rc = 1; break; }
+				uint32_t e = io.group_ends[g];
+				if(e > io.nface) e = io.nface;
+				uint32_t st = g ? io.group_ends[g - 1] : 0;
+				if(st > io.nface) st = io.nface;
+				g++;
+				start = st; end = e;
+				nfront = scan = ndel = 0; eflush = 0;
+				continue;
+			}
+			uint32_t skip = 1;
+			if(vec && scan < nfront) { rc = 4; break; }   // caller scans the flag bytes 256 at a time
+			while(scan < nfront) {                     // implicit FIFO: next queued, alive edge in id order (decoder.cpp:265-266, 278-279)
+				f = scan++;
+				skip = MG_FLAG(f);
+				if(!skip) break;
+			}
+			if(skip && ndel) {                         // delayed stack (decoder.cpp:267-269)
+				f = io.delayed[--ndel];
+				skip = MG_FLAG(f) & CLERS_DEL;
+				if(skip) continue;
+			}
+			if(!skip) { MG_LOADB(f, prev, next); MG_LOADA(f, v0, v1, v2); lp = ln = 0; have = 1; }
+			else {                                     // nothing pending: start triangle (decoder.cpp:224-259)
+				if(n == 0) break;
+				n--;
+				const uint32_t c = rg.sym(cler); cler++;
+				uint32_t last = vcount - 1, vi[3], mask = 0;
+				if(c == C_SPLIT) { mask = getbits(io.split, io.split_nwords, splitpos, 3); splitpos += 3; }
+				else bad |= (c != C_VERTEX);
+				for(int k = 0; k < 3; k++) {
+					uint32_t v;
+					if(mask & (1u << k)) {
+						v = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+						if(v >= nvert) { bad = 1; v = 0; }
+					} else if(vcount < nvert) {
+						clers_put_pred(io, vcount, last, last, last);
+						last = v = vcount++;
+					} else { bad = 1; v = 0; }
+					vi[k] = v;
+				}
+				MG_FACE(vi[0], vi[1], vi[2]);
+				const uint32_t b = nfront;
+				bad |= (nfront + 3 > cap); nfront += (nfront + 3 <= cap) ? 3u : 0u;
+				if(!bad) {
+					rg.stA(b, vi[1], vi[2], vi[0]);     rg.stB(b, b + 2, b + 1);     rg.stFl(b, 0);
+					rg.stA(b + 1, vi[2], vi[0], vi[1]); rg.stB(b + 1, b + 0, b + 2); rg.stFl(b + 1, 0);
+					rg.stA(b + 2, vi[0], vi[1], vi[2]); rg.stB(b + 2, b + 1, b + 0); rg.stFl(b + 2, 0);
+				}
+				continue;
+			}
+		}
+		while(n) {
+			if(vec && n >= runmin && end - start >= runmin) {      // a run of VERTEX / LEFT symbols ahead: CTA-wide window
+				uint32_t k = 0;
+				while(k < runmin && rg.sym(cler + k) <= (uint32_t)C_LEFT) k++;
+				if(k == runmin) { rc = 3; break; }
+			}
+			n--;
+			const uint32_t c = rg.sym(cler); cler++;
+			if(c == C_VERTEX || c == C_SPLIT) {
+				uint32_t opp, b;
+				if(c == C_VERTEX) {
+					if(vcount < nvert) { clers_put_pred(io, vcount, v1, v0, v2); opp = vcount++; } else { bad = 1; opp = 0; }
+				} else {
+					opp = getbits(io.split, io.split_nwords, splitpos, splitbits); splitpos += (uint64_t)splitbits;
+					if(opp >= nvert) { bad = 1; opp = 0; }
+				}
+				MG_NEWID(b);
+				rg.stA(b, opp, v1, v0); rg.stB(b, CLERS_NOLINK, next); rg.stFl(b, 0);   // second new edge: persistent, queued; its prev link is deferred
+				MG_SET_PREV(next, b);
+				MG_FACE(v1, v0, opp);
+				v2 = v1; v1 = opp; next = b; lp = 1; ln = 1; f = CLERS_NOID;               // first new edge: registers only
+			} else if(c == C_LEFT) {
+				if((lp | ln) && prev == next) MG_MATERIALISE();                           // 2-edge loop: deferred fields would be read
+				uint32_t pp, pn, a, t1, t2;
+				MG_LOADB(prev, pp, pn); MG_LOADA(prev, a, t1, t2);
+				(void)pn; (void)t1; (void)t2;
+				MG_SET_FLAG(prev, CLERS_DEL);
+				MG_FACE(v1, v0, a);
+				v2 = v0; v0 = a; prev = pp; lp = 1; ln = 1; f = CLERS_NOID;
+			} else if(c == C_RIGHT) {
+				if((lp | ln) && prev == next) MG_MATERIALISE();
+				uint32_t np, nn, t0, b1, t2;
+				MG_LOADB(next, np, nn); MG_LOADA(next, t0, b1, t2);
+				(void)np; (void)t0; (void)t2;
+				MG_SET_FLAG(next, CLERS_DEL);
+				MG_FACE(v1, v0, b1);
+				v2 = v1; v1 = b1; next = nn; lp = 1; ln = 1; f = CLERS_NOID;
+			} else if(c == C_END) {
+				if((lp | ln) && prev == next) MG_MATERIALISE();
+				uint32_t pp, pn, np, nn, a, t1, t2;
+				MG_LOADB(prev, pp, pn); MG_LOADB(next, np, nn); MG_LOADA(prev, a, t1, t2);
+				(void)pn; (void)np; (void)t1; (void)t2;
+				MG_SET_FLAG(prev, CLERS_DEL);
+				MG_SET_FLAG(next, CLERS_DEL);
+				MG_SET_NEXT(pp, nn);
+				MG_SET_PREV(nn, pp);
+				MG_FACE(v1, v0, a);
+				have = 0; break;
+			} else {                                       // BOUNDARY, DELAY (anything else is a corrupt stream: treated as BOUNDARY + flag)
+				bad |= (c != C_BOUNDARY && c != C_DELAY);
+				if(f == CLERS_NOID) MG_MATERIALISE();
+				if(c == C_DELAY) { if(ndel < cap) io.delayed[ndel++] = f; else bad = 1; }
+				have = 0; break;
+			}
+			if(start >= end) { have = 0; break; }          // group complete: the front is discarded (decoder.cpp:223)
+		}
+		if(have) break;                                    // budget used up in the middle of a strip / yield to a window
+	}
+	if(rc == 0 && (bad || (cler >= nclers && !(start >= end && g >= io.ngroups)))) rc = -5;   // flagged, or the stream ran dry with faces missing
+	if((rc == 3 || rc == 4) && bad) rc = -5;
+	S.cler = cler; S.vcount = vcount; S.start = start; S.end = end; S.g = g; S.nfront = nfront; S.scan = scan; S.ndel = ndel; S.bad = bad;
+	S.splitpos = splitpos; S.have = have; S.lp = lp; S.ln = ln; S.cf = f; S.v0 = v0; S.v1 = v1; S.v2 = v2; S.prev = prev; S.next = next;
+	S.eflush = eflush;
+	return rc;
+#undef MG_SET_NEXT
+#undef MG_SET_PREV
+#undef MG_LOADB
+#undef MG_LOADA
+#undef MG_FLAG
+#undef MG_SET_FLAG
+#undef MG_NEWID
+#undef MG_MATERIALISE
+#undef MG_FACE
+}
+
 // Plain-array ring policy (tests/host_emul; the kernel has its own shared-memory policy with the same interface).
 struct ArrayRings {
 	uint4_t *ra; uint2_t *rb; uint32_t *rq; uint4_t *sf; uint4_t *sp;
@@ -920,6 +1111,9 @@ struct ArrayRings {
 	uint8_t *rf;
 	CRT_HD uint32_t ldFl(uint32_t id) const { return rf[id & RM]; }
 	CRT_HD void stFl(uint32_t id, uint32_t v) { rf[id & RM] = (uint8_t)v; }
+	// v7 (merged machine): the symbol stream
+	const uint8_t *syms;
+	CRT_HD uint32_t sym(uint32_t i) const { return syms[i]; }
 };
 
 }  // namespace crtb

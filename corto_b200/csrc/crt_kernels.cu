@@ -25,37 +25,13 @@
 #include <stdlib.h>
 #include "crt_device.cuh"
 #include "crt_kernels.h"
+#include "crt_ptx.cuh"
 
 namespace crtb {
 
 // =========================================================================================================
 // small device utilities
 // =========================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-	asm volatile(
-		"{\n\t.reg .pred p;\n\t"
-		"WAIT_%=:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra DONE_%=;\n\t"
-		"bra WAIT_%=;\n\t"
-		"DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ---- decoupled look-back over a chain of tiles ------------------------------------------------------------
 // state word: bits 63..62 = 0 empty | 1 aggregate | 2 inclusive prefix; bits 61..0 = value.  One 64-bit word
 // carries flag and value together, so a relaxed volatile load/store pair is enough.  Tiles are taken in ticket
@@ -1746,19 +1722,22 @@ int launch_tun_decode(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 }
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
-	static int mode = -1;                 // CORTO_CLERS=1w selects the single-warp machine (clers_run); default: leader / follower
-	if(mode < 0) { const char *e = getenv("CORTO_CLERS"); mode = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }   // 1: one warp, 2: leader/follower scalar, 3 (default): + window steps
+	// CORTO_CLERS: 1 one warp per mesh (clers_run), 2 leader / follower warps, scalar, 3 leader / follower + 32-wide window steps,
+	// default (4): one CTA per mesh, 256-wide window steps (k_clers_cta, crt_clers_cta.cu); CORTO_RUNMIN = shortest run it takes
+	static int mode = -1, runmin = 4;
+	if(mode < 0) {
+		const char *e = getenv("CORTO_CLERS"), *r = getenv("CORTO_RUNMIN");
+		if(r && atoi(r) >= 2 && atoi(r) <= 32) runmin = atoi(r);
+		mode = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 4;
+	}
+	if(mode == 4) return launch_clers_cta(B, order, nwork, scratch, ticket, sms, (uint32_t)runmin, s);
 	const uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
 	if(mode == 1) {
 		uint32_t R = 4096, Q = 2048;
 		if(nwork > (uint32_t)sms*2u) { R = 1024; Q = 1024; }
 		const size_t smem = (size_t)R*24 + (size_t)Q*4 + 2*(size_t)CLERS_STAGE*16;
-		static size_t configured = 0;
-		if(configured < smem) {
-			cudaError_t e = cudaFuncSetAttribute(k_clers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if(e != cudaSuccess) return (int)e;
-			configured = smem;
-		}
+		cudaError_t e = cudaFuncSetAttribute(k_clers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: not cached
+		if(e != cudaSuccess) return (int)e;
 		k_clers<<<g, 32, smem, s>>>(B, order, nwork, scratch, ticket, R, Q);
 	} else {
 		// few meshes: big rings (2 CTAs per SM);  many meshes: small rings so that more serial chains share an SM
@@ -1766,12 +1745,8 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 		if(nwork > (uint32_t)sms*4u) { RB = 1024; RA = 1024; }     // really many meshes: more chains per SM beat bigger rings
 		else if(nwork <= (uint32_t)sms) { RB = 16384; RA = 2048; }   // one mesh per SM at most: the whole shared memory for its rings
 		const size_t smem = (size_t)RB*9 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
-		static size_t configured = 0;
-		if(configured < smem) {
-			cudaError_t e = cudaFuncSetAttribute(k_clers_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if(e != cudaSuccess) return (int)e;
-			configured = smem;
-		}
+		cudaError_t e = cudaFuncSetAttribute(k_clers_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: not cached
+		if(e != cudaSuccess) return (int)e;
 		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, RA, mode == 3);
 	}
 	LAUNCH_CHECK(); return 0;

@@ -111,6 +111,91 @@ static uint32_t follow_vector_host(const ClersIO &io, ArrayRings &rg, FollowStat
 	return m;
 }
 
+// ---- host transcriptions of the CTA-wide steps of k_clers_cta (cta_window / cta_pop, crt_clers_cta.cu): the same closed
+// form — ranks among the V's and the L's of the run — with threads as a loop; W = symbols per window.
+static uint32_t cta_window_host(const ClersIO &io, ArrayRings &rg, MergedState &S, uint32_t W, uint32_t R) {
+	uint32_t done = 0;
+	for(;;) {
+		const uint32_t cler = S.cler, start = S.start, end = S.end;
+		const uint32_t lim = std::min(W, std::min(io.nclers - cler, end - start));
+		uint32_t m = 0;
+		while(m < lim && rg.sym(cler + m) <= (uint32_t)C_LEFT) m++;
+		std::vector<uint32_t> nVb(m + 1, 0), nLb(m + 1, 0);
+		for(uint32_t j = 0; j < m; j++) { nVb[j + 1] = nVb[j] + (rg.sym(cler + j) == C_VERTEX); nLb[j + 1] = nLb[j] + (rg.sym(cler + j) == C_LEFT); }
+		const uint32_t nV = nVb[m], nL = nLb[m];
+		const uint32_t prev = S.prev, next = S.next, nfront = S.nfront, vcount = S.vcount, eflush = S.eflush;
+		if(m < 2 || nfront + nV > io.cap || vcount + nV > io.nvert || nfront + nV > eflush + R) return done;
+		// chain: fast path = consecutive ids, else a walk
+		std::vector<uint32_t> chain(nL + 1);
+		bool fast = true;
+		for(uint32_t k = 0; k < nL && fast; k++) {
+			const uint32_t id = prev + k;
+			if(!(id >= eflush && id < nfront && id != next)) { fast = false; break; }
+			uint32_t pk, pn; rg.ldB(id, pk, pn);
+			chain[k] = id;
+			if(k + 1 == nL) chain[nL] = pk; else if(pk != id + 1) fast = false;
+		}
+		if(nL == 0) chain[0] = prev;
+		if(!fast) {
+			uint32_t q = prev; bool ok = true;
+			for(uint32_t k = 0; k < nL; k++) {
+				chain[k] = q;
+				if(q == next || q >= nfront) { ok = false; break; }
+				uint32_t pp, pq;
+				if(q >= eflush) rg.ldB(q, pp, pq); else { pp = io.eb[q].prev; pq = io.eb[q].next; }
+				(void)pq; q = pp;
+			}
+			chain[nL] = q;
+			if(!ok) return done;
+		}
+		std::vector<uint32_t> aL(nL + 1, 0);
+		for(uint32_t k = 0; k < nL; k++) { const uint32_t id = chain[k]; uint32_t t1, t2; if(id >= eflush) rg.ldA(id, aL[k], t1, t2); else aL[k] = io.ea[id].v0; }
+		uint32_t e_v0 = S.v0, e_v1 = S.v1, e_v2 = S.v2;
+		for(uint32_t i = 0; i < m; i++) {
+			const bool isV = rg.sym(cler + i) == C_VERTEX;
+			const uint32_t rv = nVb[i], rl = nLb[i];
+			const uint32_t v0i = rl ? aL[rl - 1] : S.v0, v1i = rv ? vcount + rv - 1 : S.v1;
+			uint32_t v2i;
+			if(i == 0) v2i = S.v2;
+			else if(rg.sym(cler + i - 1) == C_VERTEX) v2i = rv > 1 ? vcount + rv - 2 : S.v1;
+			else v2i = rl > 1 ? aL[rl - 2] : S.v0;
+			const uint32_t x = vcount + rv, a = isV ? 0 : aL[rl];
+			clers_put_face(io, (size_t)(start + i)*3u, v1i, v0i, isV ? x : a);
+			if(isV) {
+				clers_put_pred(io, x, v1i, v0i, v2i);
+				const uint32_t b = nfront + rv;
+				rg.stA(b, x, v1i, v0i); rg.stB(b, rv + 1 < nV ? b + 1 : CLERS_NOLINK, rv ? b - 1 : next); rg.stFl(b, 0);
+			} else {
+				const uint32_t id = chain[rl];
+				if(id >= eflush) rg.stFl(id, CLERS_DEL); else io.fl[id] = CLERS_DEL;
+			}
+			if(i == m - 1) { e_v0 = isV ? v0i : a; e_v1 = isV ? x : v1i; e_v2 = isV ? v1i : v0i; }
+		}
+		if(nV) { if(next >= eflush) rg.stB_prev(next, nfront); else io.eb[next].prev = nfront; S.next = nfront + nV - 1; }
+		S.v0 = e_v0; S.v1 = e_v1; S.v2 = e_v2;
+		S.nfront = nfront + nV; S.vcount = vcount + nV; S.prev = chain[nL];
+		S.start = start + m; S.cler = cler + m; S.lp = S.ln = 1; S.cf = CLERS_NOID; S.have = S.start < end ? 1u : 0u;
+		done += m;
+		if(m < W || S.start >= end || S.cler >= io.nclers) return done;
+		if(S.nfront + W > eflush + R) return done;
+	}
+}
+
+static void cta_pop_host(const ClersIO &io, ArrayRings &rg, MergedState &S) {
+	uint32_t found = CLERS_NOID;
+	while(S.scan < S.nfront) {
+		const uint32_t id = S.scan++;
+		const uint32_t fl = id >= S.eflush ? rg.ldFl(id) : io.fl[id];
+		if(fl == 0) { found = id; break; }
+	}
+	if(found != CLERS_NOID) {
+		uint32_t p, q, a, b, c;
+		if(found >= S.eflush) { rg.ldB(found, p, q); rg.ldA(found, a, b, c); }
+		else { p = io.eb[found].prev; q = io.eb[found].next; a = io.ea[found].v0; b = io.ea[found].v1; c = io.ea[found].v2; }
+		S.prev = p; S.next = q; S.v0 = a; S.v1 = b; S.v2 = c; S.lp = S.ln = 0; S.have = 1; S.cf = found;
+	}
+}
+
 static std::vector<uint32_t> g_log;
 extern "C" {
 int emul_log(uint32_t *out, int cap) { int n = (int)g_log.size(); for(int i = 0; i < n && i < cap; i++) out[i] = g_log[i]; return n; }
@@ -244,6 +329,37 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		}
 		vc = F.vcount;
 		rc = rc < 0 ? rc : 0;
+	} else if(ring_q == 0) {
+		// v7 merged machine (clers_merged) with the kernel's step protocol emulated serially: scalar chunks, CTA-wide windows of W
+		// symbols (EMUL_W, default 256), CTA-wide pops, write-back of ring entries leaving the window; R = ring_r
+		const uint32_t R = (uint32_t)ring_r;
+		const uint32_t W = getenv("EMUL_W") ? (uint32_t)atoi(getenv("EMUL_W")) : 256u;
+		const uint32_t runmin = getenv("EMUL_RUNMIN") ? (uint32_t)atoi(getenv("EMUL_RUNMIN")) : 4u;
+		const bool vec = getenv("EMUL_VEC") != nullptr;
+		const uint32_t KEEP = R - 2u*W;
+		std::vector<uint4_t> ra(R); std::vector<uint2_t> rb(R); std::vector<uint8_t> rf(R);
+		ArrayRings rg{};
+		rg.ra = ra.data(); rg.rb = rb.data(); rg.rf = rf.data(); rg.RM = R - 1; rg.AM = R - 1; rg.syms = clers;
+		io.fl = (uint8_t *)order.data();
+		const int splitbits = ilog2_u32(io.nvert) + 1;
+		const int budget = (int)std::min<uint32_t>(48u, W/3u);
+		MergedState S; merged_init(S);
+		int mode = 0; bool tried = false;
+		rc = 0;
+		for(long guard = 0; guard < (1l << 40); guard++) {
+			if(mode == 1 || mode < 0) break;
+			if(S.nfront + W > S.eflush + R) {
+				const uint32_t e1 = S.nfront - KEEP;
+				for(uint32_t id = S.eflush; id < e1; id++) { const uint4_t a = ra[id & (R - 1)]; const uint2_t l = rb[id & (R - 1)]; ea[id] = EdgeA{a.x, a.y, a.z, 0}; eb[id] = EdgeB{l.x, l.y}; io.fl[id] = rf[id & (R - 1)]; }
+				S.eflush = e1;
+				continue;
+			}
+			if(mode == 3) { const uint32_t d = cta_window_host(io, rg, S, W, R); mode = 0; tried = d == 0; }
+			else if(mode == 4) { cta_pop_host(io, rg, S); mode = 0; tried = false; }
+			else { mode = clers_merged(io, rg, S, tried ? 1 : budget, vec && !tried, runmin, splitbits); tried = false; }
+		}
+		vc = S.vcount;
+		rc = mode < 0 ? mode : 0;
 	} else rc = -99;
 	for(uint32_t v = 0; v < pm.nvert; v++) for(int k = 0; k < 3; k++) prediction[v*3 + k] = pred[(size_t)v*4 + k];
 	return rc;

@@ -209,6 +209,29 @@ def test_device_cores_on_cpu(emul, name):
         os.environ.pop("EMUL_VEC", None)
 
 
+@pytest.mark.parametrize("name", [c[0] for c in cases.SMALL])
+def test_merged_clers_machine_on_cpu(emul, name):
+    """clers_merged (the scalar machine of k_clers_cta) + host transcriptions of its CTA-wide window / pop steps vs the oracle's
+    faces + predictions: scalar only and with windows, several window widths and ring sizes (tiny rings force the write-back /
+    reach-back paths), run thresholds 2 and 4."""
+    blob = _golden(name)
+    o = pyoracle.decode(blob, debug=True)
+    if not o["nface"]:
+        return
+    try:
+        for vec, W, R, runmin in ((False, 16, 64, 4), (True, 16, 64, 2), (True, 32, 128, 4), (True, 256, 1024, 4), (True, 256, 2048, 2), (True, 8, 32, 3)):
+            os.environ.pop("EMUL_VEC", None)
+            if vec:
+                os.environ["EMUL_VEC"] = "1"
+            os.environ["EMUL_W"] = str(W); os.environ["EMUL_RUNMIN"] = str(runmin)
+            faces = np.zeros((o["nface"], 3), np.uint32); pred = np.zeros((o["nvert"], 3), np.uint32)
+            rc = emul.emul_clers(_p(blob), len(blob), _p(o["clers"]), len(o["clers"]), _p(faces), _p(pred), R, 0)
+            assert rc == 0 and np.array_equal(faces, o["index"]) and np.array_equal(pred[1:], o["prediction"][1:]), (name, vec, W, R, runmin)
+    finally:
+        for k in ("EMUL_VEC", "EMUL_W", "EMUL_RUNMIN"):
+            os.environ.pop(k, None)
+
+
 # ---- multi-rank sharding over gloo, world_size 2 ---------------------------------------------------------------------
 def test_shard_lpt_balances():
     rs = np.random.RandomState(1)
