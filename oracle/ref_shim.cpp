@@ -146,6 +146,21 @@ int ref_decode_debug(const unsigned char *blob, int len,
 	} catch(const char *) { return -1; }
 }
 
+// Generic attributes decoded into caller buffers with an explicit output Format (VertexAttribute::INT32 / UINT32 / FLOAT,
+// vertex_attribute.h:184-230) through Decoder::setAttribute(name, buffer, format) (decoder.cpp:96-102).  NULL = unbound.
+int ref_decode_fmt(const unsigned char *blob, int len, void *pos, int pos_fmt, void *uv, int uv_fmt, void *radius, int radius_fmt) {
+	try {
+		Decoder dec(len, blob);
+		if(pos) dec.setAttribute("position", (char *)pos, (VertexAttribute::Format)pos_fmt);
+		if(uv) dec.setAttribute("uv", (char *)uv, (VertexAttribute::Format)uv_fmt);
+		if(radius) dec.setAttribute("radius", (char *)radius, (VertexAttribute::Format)radius_fmt);
+		std::vector<uint32_t> index((size_t)dec.nface*3 + 3);        // decodeFaces writes the index unconditionally (decoder.cpp:246-249)
+		if(dec.nface) dec.setIndex(index.data());
+		dec.decode();
+		return 0;
+	} catch(const char *) { return -1; }
+}
+
 // CPU baseline: decode `n` blobs `repeats` times with `nthreads` host threads (one crt::Decoder per
 // blob, as a user of the single-threaded reference would), all attributes bound (float normals,
 // u32 index, colours with their own component count), outputs pre-allocated per thread and reused.

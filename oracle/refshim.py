@@ -31,6 +31,7 @@ def lib():
         L.ref_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]
         L.ref_decode_debug.argtypes = L.ref_decode.argtypes + [C.c_void_p] * 4
+        L.ref_decode_fmt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ref_decode_bench.restype = C.c_double
         L.ref_decode_bench.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _lib = L
@@ -128,6 +129,27 @@ def decode(blob, index16=False, normals16=False, color_out=None, bind=None, debu
         # the reference writes nvert*out_components bytes packed at the front of the buffer
         out["color"] = out["color"].reshape(-1)[:nv * cc].reshape(nv, cc).copy()
     out["nvert"], out["nface"], out["ngroups"] = nv, nf, ng
+    return out
+
+
+def decode_formats(blob, formats, sentinel=0xA5):
+    """Generic attributes (position / uv / radius) decoded by the reference with an explicit output Format per attribute
+    (formats: name -> Format enum value; names absent from it are left unbound).  Returns dict of uint32/float32 arrays."""
+    i = info(blob)
+    nv, mask = i["nvert"], i["mask"]
+    comps = {"position": 3, "uv": 2, "radius": 1}
+    bits = {"position": 1, "uv": 8, "radius": 16}
+    out = {}
+    for name, fmt in formats.items():
+        if not (mask & bits[name]):
+            continue
+        a = np.empty((nv, comps[name]) if comps[name] > 1 else (nv,), dtype=np.float32 if fmt == 6 else np.uint32)
+        a.view(np.uint8)[...] = sentinel
+        out[name] = a
+    rc = lib().ref_decode_fmt(_p(blob), len(blob), _p(out.get("position")), formats.get("position", 6), _p(out.get("uv")), formats.get("uv", 6),
+                              _p(out.get("radius")), formats.get("radius", 6))
+    if rc:
+        raise RuntimeError("reference decoder threw")
     return out
 
 
