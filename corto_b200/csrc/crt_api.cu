@@ -69,7 +69,8 @@ struct crt_batch {
 	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
 	       o_t_vscan = 0, o_w_delta = 0, o_order = 0, o_t_cfused = 0, o_c_bits = 0;
 	// offsets inside d_zero
-	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_states = 0, z_csr = 0, z_tunbits = 0;
+	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_regular = 0, z_states = 0, z_csr = 0, z_tunbits = 0;
+	bool delta_split = false;          // irregular meshes: one warp per component (small batches)
 	size_t n_states = 0;
 	// scratch pieces
 	uint8_t *d_symbols = nullptr, *d_tunrec = nullptr; uint32_t *d_tun_used = nullptr;
@@ -385,7 +386,8 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->z_ticket = 0;
 	b->z_status = 256;
 	b->z_vcount = align_up(b->z_status + (uint64_t)n*4, 256);
-	b->z_states = align_up(b->z_vcount + (uint64_t)n*4, 256);
+	b->z_regular = align_up(b->z_vcount + (uint64_t)n*4, 256);
+	b->z_states = align_up(b->z_regular + (uint64_t)n*4, 256);
 	b->z_tunbits = align_up(b->z_states + b->n_states*8, 256);
 	b->z_csr = align_up(b->z_tunbits + ntun*8, 256);
 	uint64_t zero_total = b->z_csr + csr_bytes + 256;
@@ -438,8 +440,10 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	// (only the default warp kernel takes per-component items; the block-wide kernel, CORTO_DELTA=cta|seq, walks all components)
 	const char *force = getenv("CORTO_DELTA_SPLIT");                // 0 / 1 overrides the heuristic (tests, A/B runs)
 	const char *dmode = getenv("CORTO_DELTA");
-	const bool warp_kernel = !(dmode && (dmode[0] == 'c' || dmode[0] == 's'));
-	if(warp_kernel && (force ? force[0] == '1' : b->w_delta.size() < 2u*(size_t)b->sms)) {
+	const bool warp_kernel = dmode && dmode[0] == 'w';               // k_delta_mesh takes per-component items from the host
+	const bool want_split = force ? force[0] == '1' : b->w_delta.size() < 2u*(size_t)b->sms;
+	b->delta_split = want_split;                                      // k_delta_mesh_seg splits inside the CTA (irregular meshes only)
+	if(warp_kernel && want_split) {
 		std::vector<uint2> split;
 		for(const uint2 &w: b->w_delta)
 			for(unsigned c = 0; c < (w.y >> 16); c++) split.push_back(make_uint2(w.x, (w.y & 0xffu) | (c << 8)));
@@ -523,6 +527,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	B.group_ends = (const uint32_t *)(b->d_tables + b->o_groups);
 	B.status = (int32_t *)(b->d_zero + b->z_status);
 	B.vertex_count = (uint32_t *)(b->d_zero + b->z_vcount);
+	B.regular = (uint32_t *)(b->d_zero + b->z_regular);
 	B.tun_bits = (unsigned long long *)(b->d_zero + b->z_tunbits);
 	uint32_t *tickets = (uint32_t *)(b->d_zero + b->z_ticket);
 	uint64_t *states = (uint64_t *)(b->d_zero + b->z_states);
@@ -577,7 +582,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 		RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
 	}
 	if((rc = mark(b, "clers", k, s))) return rc;
-	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), s), !b->w_delta.empty());
+	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), b->delta_split, s), !b->w_delta.empty());
 	if((rc = mark(b, "delta", k, s))) return rc;
 	if(!b->t_faces.empty()) {                      // (the adjacency build reads the delta-decoded positions: it cannot move in front of the delta inverse)
 		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), s), true);

@@ -60,6 +60,7 @@ struct CtaShared {
 	int32_t mode;                 // next step: 0 scalar chunk, 3 window, 4 pop, 1 done, < 0 error
 	uint32_t tried;               // the last window attempt bailed: one symbol goes the scalar way
 	uint32_t flag, newprev;
+	uint32_t windowed;            // symbols that went through the CTA-wide windows
 	uint32_t wV[2][CTW], wL[2][CTW];
 	uint32_t aL[CT + 1];
 	uint32_t chain[CT + 1];
@@ -220,7 +221,7 @@ __device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const
 		if(m < (uint32_t)CT || start >= end || cler >= io.nclers) break;      // the run ended (or the group / the stream did)
 		if(nfront + nV + (uint32_t)CT > eflush + R) break;                     // ring entries have to be written back first
 	}
-	if(tid == 0) { sh.mode = 0; sh.tried = bail ? 1u : 0u; }
+	if(tid == 0) { sh.mode = 0; sh.tried = bail ? 1u : 0u; sh.windowed += done; }
 }
 
 // ---- CTA-wide pop of the implicit FIFO: 256 flag bytes per step -------------------------------------------------------------
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		const int splitbits = ilog2_u32(io.nvert) + 1;
 		const uint32_t nseg = (io.nclers + CTA_SEG - 1u)/CTA_SEG;
 		uint32_t issued = 0, ready = 0;
-		if(tid == 0) { merged_init(sh.S); sh.mode = 0; sh.tried = 0; }
+		if(tid == 0) { merged_init(sh.S); sh.mode = 0; sh.tried = 0; sh.windowed = 0; }
 		int mode;
 		for(;;) {
 			__syncthreads();                               // state, rings and outputs of the previous step are visible
@@ -329,7 +330,11 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		rg.sq += issued;
 		uint32_t vcount = sh.S.vcount;
 		const bool bad = mode < 0;
-		if(tid == 0) { if(bad) B.status[mi] = -5; B.vertex_count[mi] = vcount; }
+		if(tid == 0) {
+			if(bad) B.status[mi] = -5;
+			B.vertex_count[mi] = vcount;
+			B.regular[mi] = (uint64_t)sh.windowed*4u >= (uint64_t)io.nclers*3u ? 1u : 0u;   // the delta inverse picks its algorithm by this
+		}
 		// vertices the stream never created (corrupt / truncated input): neutral prediction so later passes stay in bounds
 		uint4 *pred = (uint4 *)M->pred_ptr;
 		if(bad) vcount = 0;

@@ -1151,6 +1151,217 @@ __global__ void __launch_bounds__(256) k_delta_mesh_cta(DevBatch B, const uint2 
 	}
 }
 
+// ---- block-wide rounds, segmented scans (the default for meshes whose CLERS stream is mostly long VERTEX / LEFT runs) ----------
+// Same skeleton as delta_mesh_cta (256 vertices per round, loads one round ahead, finals of the current / previous round in
+// shared memory), different in-round resolution.  On a regular mesh the parallelogram of vertex i is (i-1, two vertices of the
+// strip before): inside a round only the link a = i-1 is in-round, so the round is a SEGMENTED PREFIX SUM of
+// residual + outside operands, cut wherever a vertex names something else inside the round (strip starts: 1-2 cuts per round).
+//   * segment [s0, e): e = the first vertex whose in-round operands other than the link i-1 reach back to s0 or later (one
+//     ballot + one barrier); those operands then lie in earlier segments and are final in shared memory;
+//   * inside the segment: warp shuffle scan (5 steps, no barrier) + one shared-memory exchange of the warp totals;
+//   * a segment shorter than 4 vertices (irregular stretches) or a hostile operand sends the rest of the round to the
+//     sequential warps (warp_resolve), exactly as in delta_mesh_cta.
+// Two barriers per segment instead of log2(length) pointer-doubling steps with a barrier each.
+template <typename T, int NC>
+__device__ __forceinline__ void delta_mesh_seg(T *v, const uint4 *pred, const uint32_t nvert, const bool par,
+                                               uint32_t *s_fin /*[2][DB][NC]*/, uint32_t (*s_tot)[MAX_COMP] /*[8]*/, uint32_t *s_open /*[8]*/, uint32_t (*s_min)[8] /*[2]*/) {
+	const uint32_t FULL = 0xffffffffu;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t nblk = (nvert + DB - 1u)/DB;
+	uint4 pC = make_uint4(0, 0, 0, 0), pN;
+	uint32_t xC[NC], gaC[NC], gbC[NC], gcC[NC], xN[NC], gaN[NC], gbN[NC], gcN[NC];
+	auto load_round = [&](uint32_t r, uint4 &p, uint32_t (&x)[NC], uint32_t (&ga)[NC], uint32_t (&gb)[NC], uint32_t (&gc)[NC]) {
+		const uint32_t base = r*DB, i = base + tid;
+		const bool in = r < nblk && i < nvert, act = in && i > 0;
+		p = in ? pred[i] : make_uint4(0, 0, 0, 0);
+		auto far = [&](uint32_t X, bool use, uint32_t (&g)[NC]) {
+			// final in global memory (rounds < r-1), or a residual nobody has touched yet (rounds > r: hostile streams only)
+			const bool prevblk = r > 0 && X - (base - DB) < DB, inblk = X - base < DB;
+#pragma unroll
+			for(int k = 0; k < NC; k++) g[k] = (use && !prevblk && !inblk && X < nvert) ? (uint32_t)v[(size_t)X*NC + k] : 0u;
+		};
+#pragma unroll
+		for(int k = 0; k < NC; k++) x[k] = in ? (uint32_t)v[(size_t)i*NC + k] : 0u;
+		far(p.x, act, ga); far(p.y, act && par, gb); far(p.z, act && par, gc);
+	};
+	load_round(0, pC, xC, gaC, gbC, gcC);
+	uint32_t it = 0;
+	for(uint32_t r = 0; r < nblk; r++) {
+		const uint32_t cur = r & 1u, prv = cur ^ 1u;
+		const uint32_t base = r*DB, i = base + tid;
+		const bool in = i < nvert, act = in && i > 0;       // vertex 0 keeps its residual (loops start at 1)
+		load_round(r + 1, pN, xN, gaN, gbN, gcN);             // in flight while this round resolves
+		const uint32_t a = pC.x, b = pC.y, c = pC.z;
+		const bool usebc = act && par;
+		const bool a_prev = act && r > 0 && a - (base - DB) < DB, b_prev = usebc && r > 0 && b - (base - DB) < DB, c_prev = usebc && r > 0 && c - (base - DB) < DB;
+		const bool a_in = act && a - base < DB, b_in = usebc && b - base < DB, c_in = usebc && c - base < DB;
+		const uint32_t la = (a - base) & (DB - 1u), lb = (b - base) & (DB - 1u), lc = (c - base) & (DB - 1u);
+		uint32_t *fin_c = s_fin + (size_t)cur*DB*NC, *fin_p = s_fin + (size_t)prv*DB*NC;
+		uint32_t x[NC];
+#pragma unroll
+		for(int k = 0; k < NC; k++) {
+			const uint32_t fa = a_prev ? fin_p[((a - (base - DB)) & (DB - 1u))*NC + k] : gaC[k];      // (0 when inside the round or unused)
+			const uint32_t fb = b_prev ? fin_p[((b - (base - DB)) & (DB - 1u))*NC + k] : gbC[k];
+			const uint32_t fc = c_prev ? fin_p[((c - (base - DB)) & (DB - 1u))*NC + k] : gcC[k];
+			fin_c[tid*NC + k] = xC[k];                        // until it is final a vertex shows its residual, as in the in-place loop
+			x[k] = act ? xC[k] + fa + fb - fc : xC[k];
+		}
+		const bool hostile = (a_in && la >= tid) || (b_in && lb >= tid) || (c_in && lc >= tid);
+		const bool chain = a_in && la + 1u == tid;          // the link to the vertex just before me
+		int mdep = max(b_in ? (int)lb : -1, c_in ? (int)lc : -1);
+		if(a_in && !chain) mdep = max(mdep, (int)la);
+		uint32_t s = __syncthreads_or(hostile) ? 0u : DB + 1u;      // DB + 1: no fallback requested (yet)
+		if(s > DB) {
+			uint32_t s0 = 0;
+			while(s0 < DB) {
+				// e = first vertex after s0 that names (other than through its link) something at or after s0
+				const uint32_t cand = __ballot_sync(FULL, tid > s0 && mdep >= (int)s0);
+				if(lane == 0) s_min[it][warp] = cand ? warp*32u + (uint32_t)__ffs(cand) - 1u : DB;
+				__syncthreads();                               // (also: the finals of the previous segment are visible)
+				uint32_t e = DB;
+#pragma unroll
+				for(int w8 = 0; w8 < (int)(DB/32u); w8++) e = min(e, s_min[it][w8]);
+				it ^= 1u;
+				if(e - s0 < DB_MINSUB && DB - s0 > 32u) { s = s0; break; }           // irregular stretch: sequential warps from s0 on
+				const bool mine = tid >= s0 && tid < e;
+				const bool link = mine && chain && tid > s0;
+				if(mine) {
+#pragma unroll
+					for(int k = 0; k < NC; k++) {
+						if(b_in) x[k] += fin_c[lb*NC + k];            // earlier segments: final
+						if(c_in) x[k] -= fin_c[lc*NC + k];
+						if(a_in && !link) x[k] += fin_c[la*NC + k];
+					}
+				}
+				// segmented inclusive scan: a lane adds lane - d while everything in between links
+				const uint32_t linkmask = __ballot_sync(FULL, link);
+				const uint32_t heads_le = ~linkmask & (lane == 31u ? FULL : ((2u << lane) - 1u));
+				const uint32_t hp = heads_le ? 31u - (uint32_t)__clz(heads_le) : 0u;
+#pragma unroll
+				for(int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+					for(int k = 0; k < NC; k++) { const uint32_t t = __shfl_up_sync(FULL, x[k], d); if(lane >= (uint32_t)d && lane - (uint32_t)d >= hp) x[k] += t; }
+				}
+				if(lane == 31u) {
+#pragma unroll
+					for(int k = 0; k < NC; k++) s_tot[warp][k] = x[k];
+				}
+				if(lane == 0) s_open[warp] = linkmask == FULL ? 1u : 0u;
+				__syncthreads();
+				if(!heads_le && warp > 0) {                    // no head at or below me in this warp: continue the previous warp's last lane
+					uint32_t carry[NC];
+#pragma unroll
+					for(int k = 0; k < NC; k++) carry[k] = 0;
+					for(int w2 = (int)warp - 1; w2 >= 0; w2--) {
+#pragma unroll
+						for(int k = 0; k < NC; k++) carry[k] += s_tot[w2][k];
+						if(!s_open[w2]) break;
+					}
+#pragma unroll
+					for(int k = 0; k < NC; k++) x[k] += carry[k];
+				}
+				if(mine) {
+#pragma unroll
+					for(int k = 0; k < NC; k++) fin_c[tid*NC + k] = x[k];
+				}
+				s0 = e;
+			}
+			__syncthreads();                                   // the last segment's finals before anybody reads them
+		}
+		if(s <= DB) {
+			// sequential warps over [s, DB): vertices below s are final (their x is the final value and they take no further part)
+#pragma unroll 1
+			for(uint32_t ws = s >> 5; ws < DB/32u; ws++) {
+				if(warp == ws) {
+					const bool todo = act && tid >= s;
+					const bool wa_in = a_in && (la >> 5) == ws, wb_in = b_in && (lb >> 5) == ws, wc_in = c_in && (lc >> 5) == ws;
+					uint32_t ga2[NC], gb2[NC], gc2[NC];
+#pragma unroll
+					for(int k = 0; k < NC; k++) {           // in the round but outside this warp: final (before) or residual (after)
+						ga2[k] = (a_in && !wa_in) ? fin_c[la*NC + k] : 0u;
+						gb2[k] = (b_in && !wb_in) ? fin_c[lb*NC + k] : 0u;
+						gc2[k] = (c_in && !wc_in) ? fin_c[lc*NC + k] : 0u;
+					}
+					warp_resolve<NC>(x, xC, ga2, gb2, gc2, todo, wa_in, wb_in, wc_in, la & 31u, lb & 31u, lc & 31u, lane);
+#pragma unroll
+					for(int k = 0; k < NC; k++) fin_c[tid*NC + k] = x[k];
+				}
+				__syncthreads();
+			}
+		}
+		if(act) {
+#pragma unroll
+			for(int k = 0; k < NC; k++) v[(size_t)i*NC + k] = (T)x[k];
+		}
+		__syncthreads();                                   // finals of this round (shared and global) before the next round reads them
+		pC = pN;
+#pragma unroll
+		for(int k = 0; k < NC; k++) { xC[k] = xN[k]; gaC[k] = gaN[k]; gbC[k] = gbN[k]; gcC[k] = gcN[k]; }
+	}
+}
+
+// One CTA per (mesh, attribute).  Meshes the CLERS kernel found regular (most symbols in long runs) take the segmented-scan
+// rounds; the others fall back to the warp algorithm (delta_mesh_rounds) on warp 0, or on one warp per component when the
+// batch is small (`split`), the remaining warps of the CTA exit at once.
+__global__ void __launch_bounds__(256) k_delta_mesh_seg(DevBatch B, const uint2 *work, uint32_t nwork, bool split) {
+	__shared__ uint32_t s_fin[2*DB*MAX_COMP], s_tot[DB/32][MAX_COMP], s_open[DB/32], s_min[2][8];
+	const uint32_t w = blockIdx.x;
+	if(w >= nwork) return;
+	const MeshDesc *M = B.mesh + work[w].x;
+	const AttrDesc *A = &M->attr[work[w].y & 0xffu];
+	if(B.status[work[w].x]) return;
+	const uint32_t nvert = M->nvert;
+	const uint4 *pred = (const uint4 *)M->pred_ptr;
+	const bool par = (A->strategy & S_PARALLEL) && A->codec != CODEC_NORMAL;    // normals: d += d[a] only (normal_attribute.cpp:193-201)
+	const int nc = A->ncomp;
+	if(!B.regular[work[w].x]) {
+		const uint32_t warp = threadIdx.x >> 5;
+		const int lane = threadIdx.x & 31;
+		if(split) {
+			if((int)warp >= nc) return;
+			if(A->codec == CODEC_COLOR) delta_mesh_rounds<uint8_t, 1>((uint8_t *)A->work_ptr + warp, (uint32_t)nc, pred, nvert, par, lane);
+			else delta_mesh_rounds<uint32_t, 1>((uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr) + warp, (uint32_t)nc, pred, nvert, par, lane);
+			return;
+		}
+		if(warp) return;
+		if(A->codec == CODEC_COLOR) {
+			uint8_t *v = (uint8_t *)A->work_ptr;
+			switch(nc) {
+			case 1: delta_mesh_rounds<uint8_t, 1>(v, 1u, pred, nvert, par, lane); break;
+			case 2: delta_mesh_rounds<uint8_t, 2>(v, 2u, pred, nvert, par, lane); break;
+			case 3: delta_mesh_rounds<uint8_t, 3>(v, 3u, pred, nvert, par, lane); break;
+			default: delta_mesh_rounds<uint8_t, 4>(v, 4u, pred, nvert, par, lane); break;
+			}
+		} else {
+			uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
+			switch(nc) {
+			case 1: delta_mesh_rounds<uint32_t, 1>(v, 1u, pred, nvert, par, lane); break;
+			case 2: delta_mesh_rounds<uint32_t, 2>(v, 2u, pred, nvert, par, lane); break;
+			case 3: delta_mesh_rounds<uint32_t, 3>(v, 3u, pred, nvert, par, lane); break;
+			default: delta_mesh_rounds<uint32_t, 4>(v, 4u, pred, nvert, par, lane); break;
+			}
+		}
+		return;
+	}
+	if(A->codec == CODEC_COLOR) {
+		uint8_t *v = (uint8_t *)A->work_ptr;
+		switch(nc) {
+		case 1: delta_mesh_seg<uint8_t, 1>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		case 2: delta_mesh_seg<uint8_t, 2>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		case 3: delta_mesh_seg<uint8_t, 3>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		default: delta_mesh_seg<uint8_t, 4>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		}
+	} else {
+		uint32_t *v = (uint32_t *)(A->codec == CODEC_NORMAL ? A->work_ptr : A->out_ptr);
+		switch(nc) {
+		case 1: delta_mesh_seg<uint32_t, 1>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		case 2: delta_mesh_seg<uint32_t, 2>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		case 3: delta_mesh_seg<uint32_t, 3>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		default: delta_mesh_seg<uint32_t, 4>(v, pred, nvert, par, s_fin, s_tot, s_open, s_min); break;
+		}
+	}
+}
+
 // The default: one warp per chain.
 __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work, uint32_t nwork) {
 	const uint32_t w = blockIdx.x;
@@ -1751,15 +1962,18 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 	}
 	LAUNCH_CHECK(); return 0;
 }
-int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, cudaStream_t s) {
+int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, bool split, cudaStream_t s) {
 	if(nwork == 0) return 0;
 	// default: one warp per chain (k_delta_mesh; the host may have split the work list per component).  CORTO_DELTA=cta: one CTA
 	// per (mesh, attribute), 256 vertices per round (k_delta_mesh_cta) — measured 2.51 vs 2.40 ms on configs[1], 8.7 vs 6.5 ms on
 	// configs[3], 110 vs 80 ms on 64 x tarta, so it is an experiment switch, not the default; CORTO_DELTA=seq: the same kernel with
 	// every round on its sequential-warp path (tests).
+	// CORTO_DELTA=warp: k_delta_mesh for every mesh; unset: k_delta_mesh_seg (segmented-scan rounds for regular meshes, the warp
+	// algorithm for the others)
 	static int mode = -1;
-	if(mode < 0) { const char *e = getenv("CORTO_DELTA"); mode = (e && e[0] == 'c') ? 0 : ((e && e[0] == 's') ? 2 : 1); }
-	if(mode == 1) k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
+	if(mode < 0) { const char *e = getenv("CORTO_DELTA"); mode = (e && e[0] == 'c') ? 0 : ((e && e[0] == 's') ? 2 : ((e && e[0] == 'w') ? 1 : 3)); }
+	if(mode == 3) k_delta_mesh_seg<<<nwork, 256, 0, s>>>(B, work, nwork, split);
+	else if(mode == 1) k_delta_mesh<<<nwork, 32, 0, s>>>(B, work, nwork);
 	else k_delta_mesh_cta<<<nwork, 256, 0, s>>>(B, work, nwork, mode == 2);
 	LAUNCH_CHECK(); return 0;
 }
