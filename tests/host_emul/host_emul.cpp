@@ -2,6 +2,7 @@
 // (corto_b200/csrc/crt_device.cuh) plus the host directory walk, so their logic is checked without a GPU.
 // Built and driven by tests/test_host_emul.py; compares against the oracle from Python.  Not part of the product.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -136,6 +137,7 @@ static uint32_t cta_window_host(const ClersIO &io, ArrayRings &rg, MergedState &
 			if(k + 1 == nL) chain[nL] = pk; else if(pk != id + 1) fast = false;
 		}
 		if(nL == 0) chain[0] = prev;
+		if(getenv("EMUL_STATS")) { static long nf = 0, ns = 0; (fast ? nf : ns)++; if(((nf + ns) & 255) == 0) fprintf(stderr, "windows fast %ld slow %ld (m=%u nL=%u prev=%u next=%u nfront=%u eflush=%u)\n", nf, ns, m, nL, prev, next, nfront, eflush); }
 		if(!fast) {
 			uint32_t q = prev; bool ok = true;
 			for(uint32_t k = 0; k < nL; k++) {

@@ -32,6 +32,8 @@ from oracle import refshim, workloads, meshgen as mg
 distinct = [workloads._c4(s) for s in (3, 4, 5, 7, 11, 12, 13, 20)]
 big = mg.punch_hole(mg.grid(506, 99), 506)
 distinct.append(refshim.encode(big, pos_bits=14, uv_bits=12, normal_bits=10, normal_pred=2, color_bits=(6, 6, 6, 6), groups=mg.random_groups(big.nface, 4, 99))[0])
+full = mg.grid(506, 97)
+distinct.append(refshim.encode(full, pos_bits=14, uv_bits=12, normal_bits=10, normal_pred=0, color_bits=(6, 6, 6, 6), groups=mg.random_groups(full.nface, 4, 97))[0])
 two = mg.two_components(430, 98)
 distinct.append(refshim.encode(two, pos_bits=14, uv_bits=12, normal_bits=10, normal_pred=1, color_bits=(6, 6, 6, 6), groups=mg.random_groups(two.nface, 3, 98))[0])
 want = [refshim.decode(b, color_out=4) for b in distinct]
