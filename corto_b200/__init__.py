@@ -69,6 +69,7 @@ def lib():
         L.crt_batch_vert_base.restype = C.POINTER(cu64); L.crt_batch_vert_base.argtypes = [vp]
         L.crt_batch_face_base.restype = C.POINTER(cu64); L.crt_batch_face_base.argtypes = [vp]
         L.crt_batch_bind.argtypes = [vp, C.c_char_p, vp, ci, ci]
+        L.crt_batch_attr_components.argtypes = [vp, C.c_char_p]
         L.crt_batch_upload.argtypes = [vp, vp]
         L.crt_batch_rewalk.argtypes = [vp, vp]
         L.crt_batch_decode.argtypes = [vp, vp]
@@ -265,6 +266,10 @@ class BatchDecoder:
                 x.view(t.uint8).fill_(fill)
             self.out[name] = x
             _check(lib().crt_batch_bind(self._h, name.encode(), C.c_void_p(x.data_ptr()), fmt, comps))
+        for name, n in (("position", 3), ("uv", 2)):      # the arenas below are sized for these component counts
+            have = lib().crt_batch_attr_components(self._h, name.encode())
+            if have not in (0, n):
+                raise CortoError(-8, "attribute '%s' has %d components, BatchDecoder.allocate lays out %d" % (name, have, n))
         if self.mask & HAS_POSITION: mk("position", (V, 3), t.float32, FLOAT)
         if self.mask & HAS_UV: mk("uv", (V, 2), t.float32, FLOAT)
         if self.mask & HAS_NORMAL:

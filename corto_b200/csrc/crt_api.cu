@@ -19,7 +19,8 @@ using namespace crtb;
 
 // ---------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+static thread_local int g_code = 0;     // code of the last failure on this thread (crt_batch_create returns a pointer, not a code)
+static int fail(int code, const std::string &msg) { g_err = msg; g_code = code; return code; }
 static int cuda_fail(cudaError_t e, const char *what) {
 	g_err = std::string(what) + ": " + cudaGetErrorString(e);
 	return CRT_E_CUDA;
@@ -47,6 +48,7 @@ struct crt_batch {
 	std::vector<uint64_t> vert_base, face_base;
 	uint64_t total_bytes = 0;
 	std::map<std::string, Binding> binds;
+	std::map<std::string, int> comps;  // components per bound attribute name (must agree across the batch)
 
 	// host images of the device tables
 	std::vector<MeshDesc> h_mesh;
@@ -154,6 +156,12 @@ extern "C" int crt_batch_mesh_info(const crt_batch *b, int i, uint32_t *nvert, u
 	return CRT_OK;
 }
 
+extern "C" int crt_batch_attr_components(const crt_batch *b, const char *name) {
+	if(!name) return 0;
+	for(const ParsedMesh &m: b->meshes) { const int a = m.find(name); if(a >= 0) return m.attrs[a].N; }
+	return 0;
+}
+
 extern "C" int crt_batch_bind(crt_batch *b, const char *name, void *device_ptr, int format, int components) {
 	if(!name) return fail(CRT_E_ARG, "null attribute name");
 	if(!device_ptr) { b->binds.erase(name); return CRT_OK; }      // unbind: takes effect at the next crt_batch_upload / rewalk
@@ -171,6 +179,7 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 	b->t_tun.clear(); b->t_bits.clear(); b->t_dequant.clear(); b->t_faces.clear(); b->t_verts.clear(); b->t_vscan.clear(); b->t_cfused.clear();
 	b->w_delta.clear(); b->clers_order.clear();
 	b->any_border = false;
+	b->comps.clear();
 	symbols_bytes = 0; work_bytes = 0; zero_csr_bytes = 0; adj_bytes = 0;
 	work_off.assign(n, 0); csr_off.assign(n, 0); adj_off.assign(n, 0);
 	uint64_t blob_off = 0;
@@ -249,6 +258,11 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			const bool bound = it != b->binds.end();
 			if(bound) {
 				const Binding &bd = it->second;
+				// every mesh's slice of an arena is vert_base * stride: the component count behind a name has to be the same for all
+				// meshes of the batch (and is what the caller sized the arena by: crt_batch_attr_components)
+				auto nc = b->comps.find(pa.name);
+				if(nc == b->comps.end()) b->comps[pa.name] = pa.N;
+				else if(nc->second != pa.N) return fail(CRT_E_LIMIT, "attribute '" + pa.name + "' has different component counts in the meshes of this batch");
 				uint64_t stride;
 				if(pa.codec == CODEC_NORMAL) {
 					if(bd.format != CRT_FLOAT && bd.format != CRT_INT16) return fail(CRT_E_FORMAT, "Format not supported for normal attribute (float, int16 only)");
@@ -304,6 +318,8 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			if(M.position_attr < 0) return fail(CRT_E_NOPOSITION, "No position attribute found. Use DIFF normal strategy instead.");   // normal_attribute.cpp:219-221
 			if(M.attr[M.position_attr].out_format != CRT_FLOAT || !M.attr[M.position_attr].out_ptr)
 				return fail(CRT_E_NOPOSITION, "ESTIMATED/BORDER normals need the position attribute bound as float (normal_attribute.cpp:230)");
+			if(M.attr[M.position_attr].N != 3 || M.attr[M.position_attr].codec != CODEC_GENERIC)     // estimateNormals reads Point3i (normal_attribute.cpp:230)
+				return fail(CRT_E_LIMIT, "ESTIMATED/BORDER normals need a 3-component generic position attribute");
 			csr_off[i] = zero_csr_bytes;
 			zero_csr_bytes += align_up(((uint64_t)pm.nvert*3 + 2)*4, 16);      // cnt | bnd | cidx[+1] | novf
 			adj_off[i] = adj_bytes;
@@ -660,7 +676,7 @@ extern "C" int crt_shard_lpt(int n, const uint32_t *nvert, const uint32_t *nface
 // =========================================================================================================
 // single decoder with host buffers
 // =========================================================================================================
-struct HostBind { void *ptr; int format; int components; };
+struct HostBind { void *ptr; int format; int components; bool typed = false; };
 
 struct crt_decoder {
 	ParsedMesh pm;
@@ -720,16 +736,23 @@ extern "C" int crt_set_attribute(crt_decoder *d, const char *name, char *buffer,
 	int comps = d->pm.attrs[d->pm.find(name)].N;
 	auto it = d->binds.find(name);
 	if(it != d->binds.end()) comps = it->second.components;
-	d->binds[name] = HostBind{buffer, format, comps};
+	HostBind hb; hb.ptr = buffer; hb.format = format; hb.components = comps;
+	d->binds[name] = hb;
 	return 1;
 }
-extern "C" int crt_set_positions(crt_decoder *d, float *b) { return crt_set_attribute(d, "position", (char *)b, CRT_FLOAT); }
-extern "C" int crt_set_normals32(crt_decoder *d, float *b) { return crt_set_attribute(d, "normal", (char *)b, CRT_FLOAT); }
-extern "C" int crt_set_normals16(crt_decoder *d, int16_t *b) { return crt_set_attribute(d, "normal", (char *)b, CRT_INT16); }
-extern "C" int crt_set_uvs(crt_decoder *d, float *b) { return crt_set_attribute(d, "uv", (char *)b, CRT_FLOAT); }
+static int set_typed(crt_decoder *d, const char *name, void *b, int format) {
+	const int rc = crt_set_attribute(d, name, (char *)b, format);
+	if(rc) d->binds[name].typed = true;
+	return rc;
+}
+extern "C" int crt_set_positions(crt_decoder *d, float *b) { return set_typed(d, "position", b, CRT_FLOAT); }
+extern "C" int crt_set_normals32(crt_decoder *d, float *b) { return set_typed(d, "normal", b, CRT_FLOAT); }
+extern "C" int crt_set_normals16(crt_decoder *d, int16_t *b) { return set_typed(d, "normal", b, CRT_INT16); }
+extern "C" int crt_set_uvs(crt_decoder *d, float *b) { return set_typed(d, "uv", b, CRT_FLOAT); }
 extern "C" int crt_set_colors(crt_decoder *d, unsigned char *b, int components) {               // decoder.cpp:116-123
 	if(d->pm.find("color") < 0) return 0;
-	d->binds["color"] = HostBind{b, CRT_UINT8, components};
+	HostBind hb; hb.ptr = b; hb.format = CRT_UINT8; hb.components = components;
+	d->binds["color"] = hb;
 	return 1;
 }
 extern "C" void crt_set_index32(crt_decoder *d, uint32_t *b) { d->index = b; d->index16 = 0; }
@@ -739,10 +762,18 @@ extern "C" void crt_color_q(const crt_decoder *d, int qc[4]) { for(int k = 0; k 
 
 extern "C" int crt_decode(crt_decoder *d) {
 	if(!crt_device_available()) return CRT_E_CUDA;
+	// setPositions / setUvs / setNormals take float[3 nvert] / float[2 nvert] / [3 nvert] arrays (decoder.h:51-55): a header that
+	// announces another component count would write past them (the reference does, it has no checks)
+	for(const ParsedAttr &pa: d->pm.attrs) {
+		auto it = d->binds.find(pa.name);
+		if(it == d->binds.end() || !it->second.ptr || !it->second.typed) continue;
+		const int want = pa.name == "uv" ? 2 : 3;
+		if(pa.N != want) return fail(CRT_E_LIMIT, "attribute '" + pa.name + "' has " + std::to_string(pa.N) + " components, the typed setter binds " + std::to_string(want));
+	}
 	const unsigned char *blob = d->pm.blob;
 	int len = (int)d->pm.len;
 	crt_batch *b = crt_batch_create(1, &blob, &len);
-	if(!b) return CRT_E_TRUNCATED;
+	if(!b) return g_code ? g_code : CRT_E_TRUNCATED;
 	d->group_ends = b->meshes[0].group_ends; d->group_props = b->meshes[0].group_props; d->groups_known = true;
 	const ParsedMesh &pm = b->meshes[0];
 	struct Out { void *dev; void *host; size_t bytes; };

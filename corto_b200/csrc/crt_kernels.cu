@@ -119,7 +119,103 @@ __device__ __forceinline__ uint32_t cta_scan_excl_256(uint32_t v, uint32_t *s_wa
 // =========================================================================================================
 // K1  Tunstall dictionaries
 // =========================================================================================================
-__global__ void __launch_bounds__(32) k_tun_tables(DevBatch B) {
+// Warp-cooperative build of one dictionary, step for step what tun_build_seq (crt_device.cuh) does on one thread:
+//   * the most probable queue head (first strict maximum, tunstall.cpp:211-217) = warp arg-max over the n rows;
+//   * its n children (slot, probability, text = parent text + one symbol) = one lane per child;
+//   * the compaction of live slots into entry[256] (tunstall.cpp:242-255) = ballot + prefix count, 32 slots per step.
+// The low-entropy branch (run-length words, tunstall.cpp:145-194) stays on lane 0: it is rare and tiny.
+__device__ uint32_t tun_build_warp(const uint8_t *probs /* (sym,prob) pairs */, const uint32_t n, TunScratch &S, uint8_t *text, uint32_t *entry, const uint32_t lane) {
+	const uint32_t FULL = 0xffffffffu;
+	for(uint32_t i = lane; i < 512; i += 32) S.qprob[i] = 0;
+	uint32_t pos = 0, slots = 0, nwords;
+	const uint32_t p0 = (uint32_t)probs[1] << 8, p1 = (uint32_t)probs[3] << 8;
+	uint32_t run = 2, pr = (p0*p0) >> 16;
+	const uint32_t max_run = 255u/(n - 1);
+	while(pr > p1 && run < max_run) { pr = (pr*p0) >> 16; run++; }
+	__syncwarp();
+	if(run >= 16) {
+		if(lane == 0) {
+			text[pos++] = probs[0];
+			for(uint32_t k = 1; k < n; k++) {
+				for(uint32_t i = 0; i + 1 < run; i++) text[pos++] = probs[0];
+				text[pos++] = probs[2*k];
+			}
+			S.head[0] = (uint16_t)((run - 1)*n);
+			for(uint32_t k = 1; k < n; k++) S.head[k] = (uint16_t)k;
+			uint32_t q = pr;
+			for(uint32_t c = 0; c < run; c++) {
+				for(uint32_t k = 1; k < n; k++) {
+					const uint32_t sl = k + c*n, pk = (uint32_t)probs[2*k + 1] << 8;
+					S.qprob[sl] = (c == 0) ? pk : ((q*pk) >> 16);
+					S.widx[sl] = (uint16_t)(k*run - c);
+					S.wlen[sl] = (uint16_t)(c + 1);
+				}
+				q = (c == 0) ? p0 : ((q*p0) >> 16);
+			}
+			const uint32_t s0 = (run - 1)*n;
+			S.qprob[s0] = q; S.widx[s0] = 0; S.wlen[s0] = (uint16_t)run;
+		}
+		pos = 1 + (n - 1)*run;
+		nwords = 1 + run*(n - 1);
+		slots = run*n;
+	} else {
+		for(uint32_t k = lane; k < n; k += 32) {
+			S.head[k] = (uint16_t)k;
+			S.qprob[k] = (uint32_t)probs[2*k + 1] << 8;
+			S.widx[k] = (uint16_t)k; S.wlen[k] = 1;
+			text[k] = probs[2*k];
+		}
+		pos = n; slots = n; nwords = n;
+	}
+	__syncwarp();
+	while(nwords < 256) {
+		// most probable head: first strict maximum in row order
+		uint32_t bp = 0, bk = 0;
+		for(uint32_t k = lane; k < n; k += 32) { const uint32_t p = S.qprob[S.head[k]]; if(p > bp) { bp = p; bk = k; } }
+#pragma unroll
+		for(int d = 16; d; d >>= 1) {
+			const uint32_t op = __shfl_xor_sync(FULL, bp, d), ok = __shfl_xor_sync(FULL, bk, d);
+			if(op > bp || (op == bp && ok < bk)) { bp = op; bk = ok; }
+		}
+		const uint32_t best = bp ? bk : 0u;
+		const uint32_t parent = S.head[best], pp = S.qprob[parent], poff = S.widx[parent], plen = S.wlen[parent];
+		const uint32_t room = 256 - nwords;        // the child that makes word 256 ends the round (tunstall.cpp:234-235)
+		const uint32_t m = room < n ? room : n;    // children this round
+		__syncwarp();
+		for(uint32_t k = lane; k < m; k += 32) {
+			const uint32_t sl = slots + k, at = pos + k*(plen + 1);
+			if(sl < 512) {
+				S.qprob[sl] = (pp*((uint32_t)probs[2*k + 1] << 8)) >> 16;
+				S.widx[sl] = (uint16_t)at; S.wlen[sl] = (uint16_t)(plen + 1);
+			}
+			if(at + plen + 1 <= (uint32_t)TUN_TABLE_BYTES) {
+				for(uint32_t j = 0; j < plen; j++) text[at + j] = text[poff + j];
+				text[at + plen] = probs[2*k];
+			}
+		}
+		slots += m; pos += m*(plen + 1);
+		if(room > n && lane == 0) S.head[best] = (uint16_t)(parent + n);   // parent retires only if the loop ran to completion (:237-238)
+		nwords += n - 1;
+		__syncwarp();
+	}
+	if(slots > 512) slots = 512;
+	uint32_t word = 0;
+	const uint32_t below = (1u << lane) - 1u;
+	for(uint32_t s0 = 0; s0 < slots && word < 256; s0 += 32) {
+		const uint32_t sl = s0 + lane;
+		const bool keep = sl < slots && !(S.head[sl % n] > sl);
+		const uint32_t kb = __ballot_sync(FULL, keep);
+		const uint32_t at = word + __popc(kb & below);
+		if(keep && at < 256) entry[at] = (uint32_t)S.widx[sl] | ((uint32_t)S.wlen[sl] << 16);
+		word += __popc(kb);
+	}
+	if(word > 256) word = 256;
+	for(uint32_t i = word + lane; i < 256; i += 32) entry[i] = 0;
+	__syncwarp();
+	return pos < (uint32_t)TUN_TABLE_BYTES ? pos : (uint32_t)TUN_TABLE_BYTES;
+}
+
+__global__ void __launch_bounds__(32) k_tun_tables(DevBatch B, bool seq) {
 	const int t = blockIdx.x;
 	const TunDesc td = B.tun[t];
 	if(td.raw || td.nsym <= 1) return;
@@ -131,9 +227,13 @@ __global__ void __launch_bounds__(32) k_tun_tables(DevBatch B) {
 	const int lane = threadIdx.x;
 	for(uint32_t i = lane; i < 2*td.nsym; i += 32) probs[i] = B.blobs[td.probs_off + i];
 	__syncwarp();
-	if(lane == 0) s_used = tun_build_seq(probs, td.nsym, S, text, entry);
-	__syncwarp();
-	const uint32_t used16 = (s_used + 15u) & ~15u;
+	uint32_t used;
+	if(seq) {                                              // CORTO_TUN=seq: the one-thread build (A/B baseline, tests)
+		if(lane == 0) s_used = tun_build_seq(probs, td.nsym, S, text, entry);
+		__syncwarp();
+		used = s_used;
+	} else used = tun_build_warp(probs, td.nsym, S, text, entry, (uint32_t)lane);
+	const uint32_t used16 = (used + 15u) & ~15u;
 	uint8_t *rec = B.tunrec + (size_t)t*TUN_REC_BYTES;
 	uint4 *dst = (uint4 *)rec;
 	const uint4 *se = (const uint4 *)entry;
@@ -1923,7 +2023,9 @@ static inline uint32_t persistent_grid(uint32_t ntiles, int per_sm, int sms) {
 
 int launch_tun_tables(const DevBatch &B, int ntun, cudaStream_t s) {
 	if(ntun == 0) return 0;
-	k_tun_tables<<<ntun, 32, 0, s>>>(B);
+	static int seq = -1;
+	if(seq < 0) { const char *e = getenv("CORTO_TUN"); seq = (e && e[0] == 's') ? 1 : 0; }
+	k_tun_tables<<<ntun, 32, 0, s>>>(B, seq != 0);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_tun_decode(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {

@@ -3,6 +3,8 @@
 #include "crt_common.h"
 #include "../../include/corto_b200.h"
 #include <string.h>
+#include <algorithm>
+#include <vector>
 
 namespace crtb {
 
@@ -84,6 +86,19 @@ int parse_header(const uint8_t *blob, int len, ParsedMesh &m, std::string &err) 
 		a.N = (int)c.u8(); a.format = (int)c.u8(); a.strategy = (int)c.u8();
 		if(a.codec != CODEC_NORMAL && a.codec != CODEC_COLOR) a.codec = CODEC_GENERIC;                     // decoder.cpp:76-79 default branch
 		m.attrs.push_back(a);
+	}
+	// The reference keeps its attributes in a std::map<std::string, ...> (decoder.cpp:72-86): every pass, the stream walk
+	// included, visits them in byte-wise name order (decoder.cpp:168), and a repeated name keeps only its LAST header entry.
+	// Encoder-written files are sorted already; a hand-built header gets the same treatment here.
+	{
+		std::vector<ParsedAttr> uniq;
+		for(const ParsedAttr &a: m.attrs) {
+			bool dup = false;
+			for(ParsedAttr &u: uniq) if(u.name == a.name) { u = a; dup = true; }
+			if(!dup) uniq.push_back(a);
+		}
+		std::stable_sort(uniq.begin(), uniq.end(), [](const ParsedAttr &x, const ParsedAttr &y) { return x.name < y.name; });
+		m.attrs.swap(uniq);
 	}
 	m.nvert = c.u32();
 	m.nface = c.u32();

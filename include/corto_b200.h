@@ -73,7 +73,9 @@ int crt_nattr(const crt_decoder *d);
 /* attribute i in wire (= std::map name) order: name, codec, q, N, header format, strategy (decoder.cpp:62-70) */
 const char *crt_attr_info(const crt_decoder *d, int i, int *codec, float *q, int *components, int *format, int *strategy);
 
-/* Bind outputs (decoder.h:49-61).  Return 1 if the attribute exists, else 0 — like the reference's bool. */
+/* Bind outputs (decoder.h:49-61).  Return 1 if the attribute exists, else 0 — like the reference's bool.  The typed setters
+ * promise float[3 nvert] (positions, normals) / float[2 nvert] (uvs) arrays: crt_decode fails with CRT_E_LIMIT instead of
+ * writing past them when the header announces another component count (use crt_set_attribute + crt_attr_info for those). */
 int crt_set_positions(crt_decoder *d, float *buffer);
 int crt_set_normals32(crt_decoder *d, float *buffer);
 int crt_set_normals16(crt_decoder *d, int16_t *buffer);
@@ -134,6 +136,10 @@ void crt_batch_destroy(crt_batch *b);
 
 int crt_batch_count(const crt_batch *b);
 int crt_batch_mesh_info(const crt_batch *b, int i, uint32_t *nvert, uint32_t *nface, uint32_t *attr_mask);
+/* Component count the headers give attribute `name` (0 = no mesh of the batch carries it): an arena bound under that name
+ * holds components * total_verts elements.  Meshes of one batch must agree on it (crt_batch_upload fails with CRT_E_LIMIT
+ * otherwise); ESTIMATED / BORDER normals additionally need a 3-component "position". */
+int crt_batch_attr_components(const crt_batch *b, const char *name);
 uint64_t crt_batch_total_verts(const crt_batch *b);
 uint64_t crt_batch_total_faces(const crt_batch *b);
 uint64_t crt_batch_total_bytes(const crt_batch *b);     /* sum of blob lengths */

@@ -448,7 +448,7 @@ static int decode_faces(Topo *t, uint32_t start, uint32_t end) {
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* Header — src/decoder.cpp:41-89.  Attributes arrive sorted by name (std::map order == wire order). */
+/* Header — src/decoder.cpp:41-89. */
 int crt_oracle_info(const uint8_t *blob, int len, OInfo *info) {
 	(void)len;
 	if((uintptr_t)blob & 3) return -1;
@@ -467,6 +467,23 @@ int crt_oracle_info(const uint8_t *blob, int len, OInfo *info) {
 		a->codec = (int)rd32(&c);
 		uint32_t qb = rd32(&c); memcpy(&a->q, &qb, 4);
 		a->N = (int)rd8(&c); a->format = (int)rd8(&c); a->strategy = (int)rd8(&c);
+	}
+	/* std::map<std::string, VertexAttribute *> (decoder.cpp:72-86): a repeated name keeps its LAST header entry and every pass
+	 * visits the attributes in byte-wise name order (decoder.cpp:168) — which is the wire order of encoder-written files. */
+	{
+		int n = 0;
+		for(int i = 0; i < info->nattr; i++) {
+			int dup = -1;
+			for(int j = 0; j < n; j++) if(strcmp(info->attr[j].name, info->attr[i].name) == 0) dup = j;
+			if(dup >= 0) info->attr[dup] = info->attr[i]; else info->attr[n++] = info->attr[i];
+		}
+		info->nattr = n;
+		for(int i = 1; i < n; i++) {                 /* insertion sort, stable */
+			OAttrInfo t = info->attr[i];
+			int j = i;
+			while(j > 0 && strcmp(info->attr[j - 1].name, t.name) > 0) { info->attr[j] = info->attr[j - 1]; j--; }
+			info->attr[j] = t;
+		}
 	}
 	info->nvert = rd32(&c);
 	info->nface = rd32(&c);

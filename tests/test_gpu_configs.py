@@ -212,3 +212,14 @@ def test_reference_named_unity_shim(name):
         if "default/uv" in gold.files: assert np.array_equal(uv.view(np.uint32), gold["default/uv"].view(np.uint32))
         if "color_out4/color" in gold.files: assert np.array_equal(col, gold["color_out4/color"].astype(np.float32) / np.float32(255.0))
     L.DestroyDecoder(d)
+
+
+def test_unsorted_header_decodes_in_std_map_order():
+    """Header entries out of order (hand-built file): the reference walks its std::map in name order (decoder.cpp:168)."""
+    from tests.test_host import swapped_header
+    blob = refshim.aligned_blob(open(os.path.join(GOLDEN, "grid_est.crt"), "rb").read())
+    gold = np.load(os.path.join(GOLDEN, "grid_est.npz"))
+    for i, j in ((0, 2), (1, 3)):
+        got = corto_b200.Decoder(swapped_header(blob, i, j)).decode()
+        for k in ("position", "normal", "color", "uv", "radius", "index"):
+            assert np.array_equal(got[k].view(np.uint8).reshape(-1), gold["default/" + k].view(np.uint8).reshape(-1)), k

@@ -122,7 +122,7 @@ def test_tarta():
             _same("tarta/" + k, got[k], w)
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "runmin2", "runmin9", "split0", "split1", "deltacta", "deltaseq", "deltawarp", "unpackchain", "overlap1", "adjagg1"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "runmin2", "runmin9", "split0", "split1", "deltacta", "deltaseq", "deltawarp", "tunseq", "unpackchain", "overlap1", "adjagg1"])
 def test_alternative_clers_machines(mode, tmp_path):
     """CORTO_CLERS=1 (single-warp lazy-front machine) and =2 (leader/follower without window steps) stay bit-exact: they are the
     A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
@@ -154,6 +154,8 @@ print("ok")
         extra = {"CORTO_RUNMIN": mode[6:]}
     elif mode == "deltawarp":                     # the warp-per-chain delta kernel for every mesh (default: segmented-scan rounds for regular meshes)
         extra = {"CORTO_DELTA": "warp"}
+    elif mode == "tunseq":                        # the one-thread Tunstall dictionary build (default: warp-cooperative)
+        extra = {"CORTO_TUN": "seq"}
     elif mode == "deltaseq":                      # ... with every round on its sequential-warp path
         extra = {"CORTO_DELTA": "seq"}
     elif mode == "unpackchain":                   # one CTA per unpack chain (the default only for batches with >= 2 x SMs chains)

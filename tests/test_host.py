@@ -34,6 +34,44 @@ def test_abi_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def _header_attr_spans(blob):
+    """(start, end) byte spans of the attribute entries in a .crt header."""
+    b = blob.tobytes()
+    p = 9
+    nexif = int.from_bytes(b[p:p + 4], "little"); p += 4
+    for _ in range(2 * nexif):
+        p += 2 + int.from_bytes(b[p:p + 2], "little")
+    nattr = int.from_bytes(b[p:p + 4], "little"); p += 4
+    spans = []
+    for _ in range(nattr):
+        s0 = p
+        p += 2 + int.from_bytes(b[p:p + 2], "little") + 4 + 4 + 3
+        spans.append((s0, p))
+    return spans
+
+
+def swapped_header(blob, i=0, j=1):
+    """The same blob with header entries i and j exchanged (the payload stays in the original, sorted, order)."""
+    sp = _header_attr_spans(blob)
+    b = blob.tobytes()
+    (a0, a1), (b0, b1) = sp[i], sp[j]
+    out = b[:a0] + b[b0:b1] + b[a1:b0] + b[a0:a1] + b[b1:]
+    assert len(out) == len(b)
+    return refshim.aligned_blob(out)
+
+
+def test_header_attributes_follow_std_map_order():
+    """The reference visits attributes in std::map (sorted-name) order whatever the header order (decoder.cpp:72-86,168)."""
+    blob = _golden("grid_est")
+    names = list(corto_b200.Decoder(blob).attributes)
+    assert names == sorted(names) and len(names) >= 4
+    sw = swapped_header(blob, 0, 2)
+    d = corto_b200.Decoder(sw)
+    assert list(d.attributes) == names
+    for k in names:
+        assert d.attributes[k] == corto_b200.Decoder(blob).attributes[k]
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device decode must fail loudly (CRT_E_CUDA), never fall back to a CPU path."""
     if corto_b200.device_available():

@@ -105,3 +105,21 @@ def test_tunstall_table_properties():
         assert used <= 8192 and (ln >= 1).all() and ((idx + ln) <= used).all()
         words = {bytes(tab[i:i + l]) for i, l in zip(idx, ln)}
         assert len(words) >= 2
+
+
+def test_unsorted_header_follows_std_map_order():
+    """A hand-built header with attribute entries out of order: the reference decodes in std::map (sorted-name) order
+    (decoder.cpp:72-86,168), so the arrays equal those of the sorted original; the restatement does the same."""
+    if not refshim.available():
+        pytest.skip("needs the reference shim")
+    from tests.test_host import swapped_header
+    blob = refshim.aligned_blob(open(os.path.join(GOLDEN, "grid_est.crt"), "rb").read())
+    want = refshim.decode(blob)
+    for i, j in ((0, 2), (1, 3), (0, 4)):
+        sw = swapped_header(blob, i, j)
+        ref = refshim.decode(sw)
+        got = pyoracle.decode(sw)
+        for k, w in want.items():
+            if isinstance(w, np.ndarray):
+                assert np.array_equal(ref[k].view(np.uint8), w.view(np.uint8)), k
+                assert np.array_equal(got[k].view(np.uint8), w.view(np.uint8)), k
