@@ -260,9 +260,10 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 				const Binding &bd = it->second;
 				// every mesh's slice of an arena is vert_base * stride: the component count behind a name has to be the same for all
 				// meshes of the batch (and is what the caller sized the arena by: crt_batch_attr_components)
+				// (colours are written with the caller's component count, normals always as triples: their N may differ per mesh)
 				auto nc = b->comps.find(pa.name);
 				if(nc == b->comps.end()) b->comps[pa.name] = pa.N;
-				else if(nc->second != pa.N) return fail(CRT_E_LIMIT, "attribute '" + pa.name + "' has different component counts in the meshes of this batch");
+				else if(nc->second != pa.N && pa.codec == CODEC_GENERIC) return fail(CRT_E_LIMIT, "attribute '" + pa.name + "' has different component counts in the meshes of this batch");
 				uint64_t stride;
 				if(pa.codec == CODEC_NORMAL) {
 					if(bd.format != CRT_FLOAT && bd.format != CRT_INT16) return fail(CRT_E_FORMAT, "Format not supported for normal attribute (float, int16 only)");

@@ -26,7 +26,6 @@ constexpr int CT = 256;                     // threads per CTA = symbols per win
 constexpr int CTW = CT/32;
 constexpr uint32_t CTA_SEG = 1024;          // bytes per symbol segment
 constexpr uint32_t CTA_NSEG = 4;            // segments in the ring
-constexpr int CTA_SCALAR_BUDGET = 48;       // symbols per scalar chunk (each creates at most 3 ids)
 
 struct CtaRings {
 	uint32_t aA, aB, aX, aS;     // shared-space byte addresses
@@ -100,8 +99,10 @@ __device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &r
 
 // ---- CTA-wide window over a run of VERTEX / LEFT symbols -------------------------------------------------------------------
 // Runs window after window while the run lasts.  All decisions are taken on values every thread reads from shared memory, so
-// every branch around a barrier is uniform.
-__device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready) {
+// every branch around a barrier is uniform.  When the symbol right after the run is BOUNDARY / DELAY (the end of a strip on a
+// regular mesh) the window also retires the gate: the thread of the last symbol gives it a record (decoder.cpp:283, 327-331 —
+// the edge stays in the front), and the caller goes straight to the FIFO pop.  Returns 1 in that case, else 0.
+__device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready) {
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
 	const uint32_t below = (1u << lane) - 1u;
@@ -109,9 +110,10 @@ __device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const
 	const uint32_t end = sh.S.end;
 	uint32_t done = 0, it = 0;
 	bool bail = false;
+	int popnext = 0;
 	for(;; it ^= 1u) {
 		const uint32_t lim = min((uint32_t)CT, min(io.nclers - cler, end - start));
-		cta_symbols(io, rg, sh, cler, nseg, issued, ready, cler + lim);
+		cta_symbols(io, rg, sh, cler, nseg, issued, ready, min(io.nclers, cler + lim + 1u));
 		// ---- phase A: classify my symbol
 		const uint32_t c = tid < lim ? rg.sym(cler + tid) : 0xffu;
 		const bool isV = c == C_VERTEX, isL = c == C_LEFT;
@@ -119,7 +121,7 @@ __device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const
 		if(lane == 0) { sh.wV[it][w] = bV; sh.wL[it][w] = bL; }
 		__syncthreads();                                   // B1 (also: state and rings written by the previous step are visible)
 		// ---- phase B: ranks
-		const uint32_t prev = sh.S.prev, next = sh.S.next, nfront = sh.S.nfront, vcount = sh.S.vcount, eflush = sh.S.eflush;
+		const uint32_t prev = sh.S.prev, next = sh.S.next, nfront = sh.S.nfront, vcount = sh.S.vcount, eflush = sh.S.eflush, ndel = sh.S.ndel;
 		const uint32_t s_v0 = sh.S.v0, s_v1 = sh.S.v1, s_v2 = sh.S.v2;
 		uint32_t m = CT, nVb = 0, nLb = 0, nV = 0, nL = 0;
 		bool prevIsV = false;
@@ -142,7 +144,7 @@ __device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const
 		}
 		if(m > lim) m = lim;                               // (lanes past lim read 0xff: m <= lim already; belt and braces)
 		const bool mine = tid < m;
-		if(m < 2u || nfront + nV > io.cap || vcount + nV > io.nvert || nfront + nV > eflush + R) { bail = done == 0; break; }
+		if(m < 1u || nfront + nV + 1u > io.cap || vcount + nV > io.nvert || nfront + nV + 1u > eflush + R) { bail = done == 0; break; }
 		// ---- prev chain, fast path: consecutive ids prev, prev + 1, ... (the queued edges of one earlier strip)
 		uint32_t id = prev + nLb, a = 0;
 		bool good = true;
@@ -182,6 +184,13 @@ __device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const
 			}
 			__syncthreads();
 		}
+		// ---- the symbol after the run: BOUNDARY / DELAY retire the gate right here
+		const uint32_t newprev = sh.newprev;
+		const uint32_t nextf = nV ? nfront + nV - 1u : next;   // right-hand neighbour of the gate after the run
+		const uint32_t gid = nfront + nV;                      // id of the gate's record, if it gets one
+		uint32_t cm = 0xffu;
+		if(cler + m < io.nclers && start + m < end) cm = rg.sym(cler + m);
+		const bool gend = (cm == C_BOUNDARY || (cm == C_DELAY && ndel < io.cap)) && newprev != nextf && newprev < nfront;
 		// ---- phase C: labels, outputs, ring records
 		if(mine) {
 			const uint32_t v0i = nLb ? sh.aL[nLb - 1u] : s_v0;
@@ -199,36 +208,50 @@ __device__ void cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const
 				((uint4 *)io.pred)[x] = make_uint4(v1i, v0i, v2i, 0u);
 				const uint32_t b = nfront + nVb;
 				rg.stA(b, x, v1i, v0i);
-				rg.stB(b, nVb + 1u < nV ? b + 1u : CLERS_NOLINK, nVb ? b - 1u : next);
+				rg.stB(b, nVb + 1u < nV ? b + 1u : (gend ? gid : CLERS_NOLINK), nVb ? b - 1u : next);
 				rg.stFl(b, 0u);
 			} else {
 				if(id >= eflush) rg.stFl(id, CLERS_DEL); else lead_g_set_flag(io.fl, id, CLERS_DEL);
 			}
-			if(tid == m - 1u) { sh.S.v0 = isL ? a : v0i; sh.S.v1 = isV ? x : v1i; sh.S.v2 = isV ? v1i : v0i; }
+			if(tid == m - 1u) {
+				const uint32_t g0 = isL ? a : v0i, g1 = isV ? x : v1i, g2 = isV ? v1i : v0i;     // the gate after the run
+				sh.S.v0 = g0; sh.S.v1 = g1; sh.S.v2 = g2;
+				if(gend) {
+					rg.stA(gid, g0, g1, g2); rg.stB(gid, newprev, nextf); rg.stFl(gid, CLERS_NQ);
+					if(newprev >= eflush) rg.stB_next(newprev, gid); else clers_g_set_next(io.eb, newprev, gid);
+					if(nV == 0) { if(next >= eflush) rg.stB_prev(next, gid); else clers_g_set_prev(io.eb, next, gid); }
+					if(cm == C_DELAY) io.delayed[ndel] = gid;
+				}
+			}
 		}
 		if(tid == 0) {
 			if(nV) {
 				if(next >= eflush) rg.stB_prev(next, nfront); else clers_g_set_prev(io.eb, next, nfront);
-				sh.S.next = nfront + nV - 1u;
+				sh.S.next = nextf;
 			}
-			sh.S.nfront = nfront + nV; sh.S.vcount = vcount + nV;
-			sh.S.prev = sh.newprev;
-			sh.S.start = start + m; sh.S.cler = cler + m;
+			sh.S.nfront = nfront + nV + (gend ? 1u : 0u); sh.S.vcount = vcount + nV;
+			sh.S.prev = newprev;
+			sh.S.start = start + m; sh.S.cler = cler + m + (gend ? 1u : 0u);
 			sh.S.lp = sh.S.ln = 1; sh.S.cf = CLERS_NOID;
-			sh.S.have = start + m < end ? 1u : 0u;
+			sh.S.have = (!gend && start + m < end) ? 1u : 0u;
+			if(gend && cm == C_DELAY) sh.S.ndel = ndel + 1u;
 		}
 		cler += m; start += m; done += m;
+		if(gend) { popnext = 1; break; }
 		if(m < (uint32_t)CT || start >= end || cler >= io.nclers) break;      // the run ended (or the group / the stream did)
-		if(nfront + nV + (uint32_t)CT > eflush + R) break;                     // ring entries have to be written back first
+		if(nfront + nV + (uint32_t)CT + 1u > eflush + R) break;                // ring entries have to be written back first
 	}
-	if(tid == 0) { sh.mode = 0; sh.tried = bail ? 1u : 0u; sh.windowed += done; }
+	if(tid == 0) { sh.tried = bail ? 1u : 0u; sh.windowed += done; }
+	return popnext;
 }
 
 // ---- CTA-wide pop of the implicit FIFO: 256 flag bytes per step -------------------------------------------------------------
-__device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh) {
+// The popped edge becomes the gate.  When the symbol waiting for it is BOUNDARY / DELAY (decoder.cpp:283, 327-331: the edge keeps
+// its record, nothing else changes) the symbol is consumed right here and the scan goes on from the next id.
+__device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t nseg, uint32_t &issued, uint32_t &ready) {
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-	uint32_t scan = sh.S.scan;
+	uint32_t scan = sh.S.scan, cler = sh.S.cler, ndel = sh.S.ndel;
 	const uint32_t nfront = sh.S.nfront, eflush = sh.S.eflush;
 	uint32_t found = CLERS_NOID, it = 0;
 	while(scan < nfront) {
@@ -238,14 +261,25 @@ __device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh) {
 		const uint32_t alive = __ballot_sync(FULL, fl == 0u);
 		if(lane == 0) sh.wV[it][w] = alive;
 		__syncthreads();
+		found = CLERS_NOID;
 #pragma unroll
 		for(int j = CTW - 1; j >= 0; j--) { const uint32_t x = sh.wV[it][j]; if(x) found = scan + (uint32_t)j*32u + (uint32_t)__ffs(x) - 1u; }
-		if(found != CLERS_NOID) { scan = found + 1u; break; }
-		scan += CT;
 		it ^= 1u;
+		if(found == CLERS_NOID) { scan += CT; continue; }
+		scan = found + 1u;
+		uint32_t c = 0xffu;
+		if(cler < io.nclers) { cta_symbols(io, rg, sh, cler, nseg, issued, ready, cler + 1u); c = rg.sym(cler); }
+		if(c == C_BOUNDARY || (c == C_DELAY && ndel < io.cap)) {
+			if(c == C_DELAY) { if(tid == 0) io.delayed[ndel] = found; ndel++; }
+			cler++;
+			found = CLERS_NOID;
+			continue;
+		}
+		break;
 	}
 	if(tid == 0) {
 		sh.S.scan = scan < nfront ? scan : nfront;
+		sh.S.cler = cler; sh.S.ndel = ndel;
 		if(found != CLERS_NOID) {
 			uint32_t p, q, a, b, c;
 			if(found >= eflush) { rg.ldB(found, p, q); rg.ldA(found, a, b, c); }
@@ -253,7 +287,7 @@ __device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh) {
 			sh.S.prev = p; sh.S.next = q; sh.S.v0 = a; sh.S.v1 = b; sh.S.v2 = c;
 			sh.S.lp = sh.S.ln = 0; sh.S.have = 1; sh.S.cf = found;
 		}
-		sh.mode = 0; sh.tried = 0;
+		sh.tried = 0;
 	}
 }
 
@@ -268,8 +302,10 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		rg.aA = sbase; rg.aB = sbase + R*16u; rg.aX = rg.aB + R*8u; rg.aS = rg.aX + R;
 		rg.RM = R - 1u; rg.sq = 0;
 	}
+	(void)runmin;
 	if(tid == 0) for(uint32_t k = 0; k < CTA_NSEG; k++) mbar_init(&sh.bar[k], 1);
-	const uint32_t KEEP = R - 2u*(uint32_t)CT;             // ring entries kept after a write-back
+	const uint32_t KEEP = R - 4u*(uint32_t)CT;             // ring entries kept after a write-back
+	const uint32_t ROOM = (uint32_t)CT + 4u;               // ids one step can allocate: a window (+ the gate's record), a start triangle
 	for(;;) {
 		__syncthreads();
 		if(tid == 0) sh.work = atomicAdd(ticket, 1u);
@@ -302,9 +338,9 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		for(;;) {
 			__syncthreads();                               // state, rings and outputs of the previous step are visible
 			mode = sh.mode;
-			if(mode == 1 || mode < 0) break;
+			if(mode) break;
 			const uint32_t cler = sh.S.cler, nfront = sh.S.nfront, eflush = sh.S.eflush;
-			if(nfront + (uint32_t)CT > eflush + R) {       // write ring entries leaving the window back to the reach-back store
+			if(nfront + ROOM > eflush + R) {               // write ring entries leaving the window back to the reach-back store
 				const uint32_t e1 = nfront - KEEP;
 				for(uint32_t id = eflush + tid; id < e1; id += CT) {
 					uint32_t a, b, c, p, n;
@@ -315,12 +351,22 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 				if(tid == 0) sh.S.eflush = e1;
 				continue;
 			}
-			cta_symbols(io, rg, sh, cler, nseg, issued, ready, min(io.nclers, cler + (uint32_t)CT + 64u));
-			if(mode == 3) cta_window(io, rg, sh, R, nseg, issued, ready);
-			else if(mode == 4) cta_pop(io, rg, sh);
+			const uint32_t have = sh.S.have, tried = sh.tried;
+			const bool canpop = sh.S.start < sh.S.end && sh.S.scan < nfront;
+			cta_symbols(io, rg, sh, cler, nseg, issued, ready, min(io.nclers, cler + 2u));
+			const uint32_t c0 = cler < io.nclers ? rg.sym(cler) : 0xffu;
+			if(have && !tried && c0 <= (uint32_t)C_LEFT) {
+				if(cta_window(io, rg, sh, R, nseg, issued, ready)) {
+					__syncthreads();                       // the flags this window set are visible to the scan
+					cta_pop(io, rg, sh, nseg, issued, ready);
+				}
+			} else if(!have && canpop) cta_pop(io, rg, sh, nseg, issued, ready);
 			else if(tid == 0) {
-				const bool tried = sh.tried != 0;
-				int rc = clers_merged(io, rg, sh.S, tried ? 1 : CTA_SCALAR_BUDGET, !tried, runmin, splitbits);
+				// everything else, one symbol at a time: RIGHT, END, SPLIT, BOUNDARY / DELAY on a gate the window did not retire, start
+				// triangles, group changes, the delayed stack, and the symbol a window declined
+				const uint32_t c0 = sh.S.cler, s0 = sh.S.start, g0 = sh.S.g, h0 = sh.S.have, n0 = sh.S.ndel, q0 = sh.S.scan;
+				int rc = clers_merged(io, rg, sh.S, 1, false, 2u, splitbits);
+				if(rc == 0 && c0 == sh.S.cler && s0 == sh.S.start && g0 == sh.S.g && h0 == sh.S.have && n0 == sh.S.ndel && q0 == sh.S.scan) rc = -5;   // no progress
 				sh.tried = 0;
 				sh.mode = rc;
 			}

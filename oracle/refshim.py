@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_ref", "libcorto_ref.so")
+_SO = os.environ.get("CORTO_REFSHIM_SO") or os.path.join(_HERE, "_ref", "libcorto_ref.so")   # override: sanitizer builds
 TARTA = os.path.join(_HERE, "_ref", "tarta.crt")
 _lib = None
 

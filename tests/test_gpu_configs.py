@@ -84,8 +84,9 @@ def test_c5_one_10m_vertex_mesh():
         if isinstance(w, np.ndarray):
             assert got[k].shape == w.shape
             assert pyoracle.fnv1a64(got[k]) == pyoracle.fnv1a64(w), k
-    want16 = refshim.decode(blob, normals16=True, bind=["position", "normal"])
-    got16 = corto_b200.Decoder(blob).decode(normals16=True, bind=["position", "normal"])
+    # (the index has to stay bound: the reference's decodeFaces writes through faces32 / faces16 unconditionally)
+    want16 = refshim.decode(blob, normals16=True, bind=["position", "normal", "index"])
+    got16 = corto_b200.Decoder(blob).decode(normals16=True, bind=["position", "normal", "index"])
     assert pyoracle.fnv1a64(got16["normal"]) == pyoracle.fnv1a64(want16["normal"])
 
 
