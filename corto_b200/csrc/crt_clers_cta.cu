@@ -22,14 +22,16 @@ namespace crtb {
 
 extern __shared__ __align__(16) uint8_t cta_smem[];
 
-constexpr int CT = 256;                     // threads per CTA = symbols per window step
+constexpr int CT = 256;                     // threads per CTA
 constexpr int CTW = CT/32;
-constexpr uint32_t CTA_SEG = 1024;          // bytes per symbol segment
-constexpr uint32_t CTA_NSEG = 4;            // segments in the ring
+constexpr uint32_t CTA_SEG = 512;           // bytes per symbol segment
+constexpr uint32_t CTA_SEG_LOG = 9;
+constexpr uint32_t CTA_NSEG = 8;            // segments in the ring
+constexpr uint32_t CTA_NSEG_LOG = 3;
 
 struct CtaRings {
 	uint32_t aA, aB, aX, aS;     // shared-space byte addresses
-	uint32_t RM, sq;             // ring mask; sequence number of this mesh's segment 0 (slot = (sq + seg) & 3)
+	uint32_t RM, sq;             // ring mask; sequence number of this mesh's segment 0 (slot = (sq + seg) & 7)
 	__device__ __forceinline__ void ldA(uint32_t id, uint32_t &a, uint32_t &b, uint32_t &c) const {
 		[[maybe_unused]] uint32_t d; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(aA + ((id & RM) << 4)));
 	}
@@ -46,34 +48,35 @@ struct CtaRings {
 	__device__ __forceinline__ void stB_prev(uint32_t id, uint32_t p) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3)), "r"(p) : "memory"); }
 	__device__ __forceinline__ void stB_next(uint32_t id, uint32_t n) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(aB + ((id & RM) << 3) + 4u), "r"(n) : "memory"); }
 	__device__ __forceinline__ uint32_t ldFl(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aX + (id & RM))); return v; }
+	__device__ __forceinline__ uint32_t ldFl4(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aX + (id & RM))); return v; }   // id % 4 == 0
 	__device__ __forceinline__ void stFl(uint32_t id, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(aX + (id & RM)), "r"(v) : "memory"); }
 	__device__ __forceinline__ uint32_t sym(uint32_t i) const {
 		uint32_t v;
-		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aS + (((sq + (i >> 10)) & (CTA_NSEG - 1u)) << 10) + (i & (CTA_SEG - 1u))));
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aS + (((sq + (i >> CTA_SEG_LOG)) & (CTA_NSEG - 1u)) << CTA_SEG_LOG) + (i & (CTA_SEG - 1u))));
 		return v;
 	}
 };
 
-struct CtaShared {
+template <int NH> struct CtaShared {
 	MergedState S;
-	int32_t mode;                 // next step: 0 scalar chunk, 3 window, 4 pop, 1 done, < 0 error
-	uint32_t tried;               // the last window attempt bailed: one symbol goes the scalar way
+	int32_t mode;                 // 0 running, 1 done, < 0 error
+	uint32_t tried;               // the last window attempt declined its first symbol: it goes the scalar way
 	uint32_t flag, newprev;
 	uint32_t windowed;            // symbols that went through the CTA-wide windows
-	uint32_t wV[2][CTW], wL[2][CTW];
-	uint32_t aL[CT + 1];
-	uint32_t chain[CT + 1];
+	uint32_t pk[2][32];           // per virtual warp of a window: first stop | V count << 8 | L count << 16 (counts before the stop)
+	uint32_t wA[2][CTW];          // pop: first alive id per warp
+	uint32_t aL[NH*CT + 1];       // prev-chain ids (slow path only), then the label v0 of the k-th edge the run's LEFTs consume
 	uint32_t work;
 	alignas(8) uint64_t bar[CTA_NSEG];
 };
 
 // ---- symbol segments -----------------------------------------------------------------------------------------------------
-// Segment s of the current mesh (symbols [1024 s, 1024 s + 1024)) is copy number sq + s of this CTA: slot (sq + s) & 3, and
-// the ((sq + s) >> 2)-th use of that slot's mbarrier.  Segments up to (cler >> 10) + 3 are in flight (the slot of segment s + 4
+// Segment s of the current mesh (symbols [512 s, 512 s + 512)) is copy number sq + s of this CTA: slot (sq + s) & 7, and
+// the ((sq + s) >> 3)-th use of that slot's mbarrier.  Segments up to (cler >> 9) + 7 are in flight (the slot of segment s + 8
 // is free once the cursor has left segment s).  `issued` / `ready` are uniform counters every thread keeps in registers.
-__device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &rg, CtaShared &sh, uint32_t cler, uint32_t nseg, uint32_t &issued, uint32_t &ready,
+__device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &rg, uint64_t *bar, uint32_t cler, uint32_t nseg, uint32_t &issued, uint32_t &ready,
                                             uint32_t upto /* symbols below this index must be readable */) {
-	const uint32_t want = min(nseg, (cler >> 10) + CTA_NSEG);
+	const uint32_t want = min(nseg, (cler >> CTA_SEG_LOG) + CTA_NSEG);
 	if(issued < want) {
 		if(threadIdx.x == 0) {
 			fence_proxy_async();
@@ -82,80 +85,93 @@ __device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &r
 				uint32_t bytes = io.nclers - s*CTA_SEG;
 				if(bytes > CTA_SEG) bytes = CTA_SEG;
 				bytes = (bytes + 15u) & ~15u;                      // the symbol arena pads every block (crt_api.cu: add_block)
-				mbar_expect_tx(&sh.bar[slot], bytes);
-				tma_bulk_g2s(cta_smem + (rg.aS - smem_u32(cta_smem)) + slot*CTA_SEG, io.clers + (size_t)s*CTA_SEG, bytes, &sh.bar[slot]);
+				mbar_expect_tx(&bar[slot], bytes);
+				tma_bulk_g2s(cta_smem + (rg.aS - smem_u32(cta_smem)) + slot*CTA_SEG, io.clers + (size_t)s*CTA_SEG, bytes, &bar[slot]);
 			}
 		}
 		issued = want;
 	}
-	uint32_t need = (upto + CTA_SEG - 1u) >> 10;
+	uint32_t need = (upto + CTA_SEG - 1u) >> CTA_SEG_LOG;
 	if(need > issued) need = issued;
 	while(ready < need) {
 		const uint32_t q = rg.sq + ready;
-		mbar_wait(&sh.bar[q & (CTA_NSEG - 1u)], (q >> 2) & 1u);
+		mbar_wait(&bar[q & (CTA_NSEG - 1u)], (q >> CTA_NSEG_LOG) & 1u);
 		ready++;
 	}
 }
 
 // ---- CTA-wide window over a run of VERTEX / LEFT symbols -------------------------------------------------------------------
-// Runs window after window while the run lasts.  All decisions are taken on values every thread reads from shared memory, so
-// every branch around a barrier is uniform.  When the symbol right after the run is BOUNDARY / DELAY (the end of a strip on a
-// regular mesh) the window also retires the gate: the thread of the last symbol gives it a record (decoder.cpp:283, 327-331 —
-// the edge stays in the front), and the caller goes straight to the FIFO pop.  Returns 1 in that case, else 0.
-__device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready) {
+// One window = NH*256 symbols; thread t takes symbols t, t + 256, ... ("virtual warp" w + 8 h holds symbols 32 (w + 8 h) ..).
+// A run of VERTEX / LEFT symbols is a closed form of two prefix counts (crt_device.cuh, "v7"); the counts are one packed word per
+// virtual warp, scanned with shuffles by every warp.  Runs window after window while the run lasts.  All decisions are taken
+// on values every thread reads from shared memory, so every branch around a barrier is uniform.  When the symbol right after
+// the run is BOUNDARY / DELAY (the end of a strip on a regular mesh) the window also retires the gate: the thread of the last
+// symbol gives it a record (decoder.cpp:283, 327-331 — the edge stays in the front) and the caller goes straight to the FIFO
+// pop.  Returns 1 in that case, else 0.  cler / start: uniform cursors, updated.
+template <int NH>
+__device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready,
+                          uint32_t &cler, uint32_t &start, const uint32_t end) {
+	constexpr uint32_t WS = NH*CT, NVW = NH*CTW;
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
 	const uint32_t below = (1u << lane) - 1u;
-	uint32_t cler = sh.S.cler, start = sh.S.start;
-	const uint32_t end = sh.S.end;
 	uint32_t done = 0, it = 0;
 	bool bail = false;
 	int popnext = 0;
 	for(;; it ^= 1u) {
-		const uint32_t lim = min((uint32_t)CT, min(io.nclers - cler, end - start));
-		cta_symbols(io, rg, sh, cler, nseg, issued, ready, min(io.nclers, cler + lim + 1u));
-		// ---- phase A: classify my symbol
-		const uint32_t c = tid < lim ? rg.sym(cler + tid) : 0xffu;
-		const bool isV = c == C_VERTEX, isL = c == C_LEFT;
-		const uint32_t bV = __ballot_sync(FULL, isV), bL = __ballot_sync(FULL, isL);
-		if(lane == 0) { sh.wV[it][w] = bV; sh.wL[it][w] = bL; }
+		const uint32_t lim = min(WS, min(io.nclers - cler, end - start));
+		cta_symbols(io, rg, sh.bar, cler, nseg, issued, ready, min(io.nclers, cler + lim + 1u));
+		// ---- phase A: classify my symbols, one packed word per virtual warp
+		uint32_t bV[NH], bL[NH], psym[NH];
+#pragma unroll
+		for(int h = 0; h < NH; h++) {
+			const uint32_t s = tid + (uint32_t)h*CT;
+			const uint32_t c = s < lim ? rg.sym(cler + s) : 0xffu;
+			psym[h] = (lane == 0 && s > 0 && s < lim) ? rg.sym(cler + s - 1u) : 0xffu;       // the symbol before my warp's first
+			bV[h] = __ballot_sync(FULL, c == C_VERTEX); bL[h] = __ballot_sync(FULL, c == C_LEFT);
+			const uint32_t stop = ~(bV[h] | bL[h]);
+			const uint32_t k = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+			const uint32_t pm = stop ? (1u << k) - 1u : FULL;
+			if(lane == 0) sh.pk[it][w + (uint32_t)h*CTW] = k | ((uint32_t)__popc(bV[h] & pm) << 8) | ((uint32_t)__popc(bL[h] & pm) << 16);
+		}
 		__syncthreads();                                   // B1 (also: state and rings written by the previous step are visible)
 		// ---- phase B: ranks
 		const uint32_t prev = sh.S.prev, next = sh.S.next, nfront = sh.S.nfront, vcount = sh.S.vcount, eflush = sh.S.eflush, ndel = sh.S.ndel;
 		const uint32_t s_v0 = sh.S.v0, s_v1 = sh.S.v1, s_v2 = sh.S.v2;
-		uint32_t m = CT, nVb = 0, nLb = 0, nV = 0, nL = 0;
-		bool prevIsV = false;
+		const uint32_t e = lane < NVW ? sh.pk[it][lane] : 32u;
+		const uint32_t stopb = __ballot_sync(FULL, (e & 0x3fu) < 32u);
+		const uint32_t ws = stopb ? (uint32_t)__ffs(stopb) - 1u : 32u;            // first virtual warp with a stop
+		const uint32_t cnt = lane <= ws ? (((e >> 8) & 0x3fu) | (((e >> 16) & 0x3fu) << 16)) : 0u;
+		uint32_t incl = cnt;
 #pragma unroll
-		for(int j = 0; j < CTW; j++) {
-			uint32_t v = sh.wV[it][j], l = sh.wL[it][j];
-			if(m == CT) {
-				const uint32_t stop = ~(v | l);
-				if(stop) {
-					const uint32_t k = (uint32_t)__ffs(stop) - 1u;
-					m = (uint32_t)j*32u + k;
-					const uint32_t pm = (1u << k) - 1u;
-					v &= pm; l &= pm;
-				}
-			} else { v = 0; l = 0; }
-			nV += __popc(v); nL += __popc(l);
-			if((uint32_t)j < w) { nVb += __popc(v); nLb += __popc(l); }
-			else if((uint32_t)j == w) { nVb += __popc(v & below); nLb += __popc(l & below); if(lane) prevIsV = (v >> (lane - 1u)) & 1u; }
-			if((uint32_t)j + 1u == w && lane == 0) prevIsV = (v >> 31) & 1u;
-		}
-		if(m > lim) m = lim;                               // (lanes past lim read 0xff: m <= lim already; belt and braces)
-		const bool mine = tid < m;
-		if(m < 1u || nfront + nV + 1u > io.cap || vcount + nV > io.nvert || nfront + nV + 1u > eflush + R) { bail = done == 0; break; }
+		for(int d = 1; d < (int)NVW; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if(lane >= (uint32_t)d) incl += t; }
+		const uint32_t tot = __shfl_sync(FULL, incl, NVW - 1u);
+		const uint32_t nV = tot & 0xffffu, nL = tot >> 16;
+		const uint32_t excl = incl - cnt;
+		uint32_t m = WS;
+		{ const uint32_t ek = __shfl_sync(FULL, e, ws & 31u); if(ws < NVW) m = ws*32u + (ek & 0x3fu); }
+		if(m > lim) m = lim;                               // (symbols past lim read 0xff: m <= lim already; belt and braces)
+		if(m < 1u || nfront + nV + 1u > io.cap || vcount + nV > io.nvert) { bail = done == 0; break; }
+		if(nfront + nV + 1u > eflush + R) break;           // the caller writes ring entries back first
+		uint32_t nVb[NH], nLb[NH], id[NH], a[NH];
 		// ---- prev chain, fast path: consecutive ids prev, prev + 1, ... (the queued edges of one earlier strip)
-		uint32_t id = prev + nLb, a = 0;
 		bool good = true;
-		if(mine && isL) {
-			good = id >= eflush && id < nfront && id != next;
-			if(good) {
-				uint32_t pk, pn;
-				rg.ldB(id, pk, pn);
-				a = rg.ldA0(id);
-				if(nLb + 1u == nL) sh.newprev = pk; else good = pk == id + 1u;
-				sh.aL[nLb] = a;
+#pragma unroll
+		for(int h = 0; h < NH; h++) {
+			const uint32_t base = __shfl_sync(FULL, excl, w + (uint32_t)h*CTW);
+			nVb[h] = (base & 0xffffu) + (uint32_t)__popc(bV[h] & below);
+			nLb[h] = (base >> 16) + (uint32_t)__popc(bL[h] & below);
+			id[h] = prev + nLb[h]; a[h] = 0;
+			if(tid + (uint32_t)h*CT < m && ((bL[h] >> lane) & 1u)) {
+				bool g = id[h] >= eflush && id[h] < nfront && id[h] != next;
+				if(g) {
+					uint32_t pk, pn;
+					rg.ldB(id[h], pk, pn);
+					a[h] = rg.ldA0(id[h]);
+					if(nLb[h] + 1u == nL) sh.newprev = pk; else g = pk == id[h] + 1u;
+					sh.aL[nLb[h]] = a[h];
+				}
+				good = good && g;
 			}
 		}
 		if(nL == 0 && tid == 0) sh.newprev = prev;
@@ -165,7 +181,7 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 			if(tid == 0) {
 				uint32_t q = prev, ok = 1;
 				for(uint32_t k = 0; k < nL; k++) {
-					sh.chain[k] = q;
+					sh.aL[k] = q;
 					if(q == next || q >= nfront) { ok = 0; break; }
 					uint32_t pp, pq;
 					if(q >= eflush) rg.ldB(q, pp, pq); else { const uint2_t t_ = lead_g_load(io.eb, q); pp = t_.x; pq = t_.y; }
@@ -177,10 +193,13 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 			}
 			__syncthreads();
 			if(!sh.flag) { bail = done == 0; break; }
-			if(mine && isL) {
-				id = sh.chain[nLb];
-				if(id >= eflush) a = rg.ldA0(id); else a = follow_g_load(io.ea, id).x;
-				sh.aL[nLb] = a;
+#pragma unroll
+			for(int h = 0; h < NH; h++) {
+				if(tid + (uint32_t)h*CT < m && ((bL[h] >> lane) & 1u)) {
+					id[h] = sh.aL[nLb[h]];
+					if(id[h] >= eflush) a[h] = rg.ldA0(id[h]); else a[h] = follow_g_load(io.ea, id[h]).x;
+					sh.aL[nLb[h]] = a[h];
+				}
 			}
 			__syncthreads();
 		}
@@ -192,35 +211,42 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 		if(cler + m < io.nclers && start + m < end) cm = rg.sym(cler + m);
 		const bool gend = (cm == C_BOUNDARY || (cm == C_DELAY && ndel < io.cap)) && newprev != nextf && newprev < nfront;
 		// ---- phase C: labels, outputs, ring records
-		if(mine) {
-			const uint32_t v0i = nLb ? sh.aL[nLb - 1u] : s_v0;
-			const uint32_t v1i = nVb ? vcount + nVb - 1u : s_v1;
-			uint32_t v2i;
-			if(tid == 0) v2i = s_v2;
-			else if(prevIsV) v2i = nVb > 1u ? vcount + nVb - 2u : s_v1;
-			else v2i = nLb > 1u ? sh.aL[nLb - 2u] : s_v0;
-			const uint32_t x = vcount + nVb;
-			const uint32_t third = isV ? x : a;
-			const size_t at = (size_t)(start + tid)*3u;
-			if(io.faces16) { io.faces16[at] = (uint16_t)v1i; io.faces16[at + 1] = (uint16_t)v0i; io.faces16[at + 2] = (uint16_t)third; }
-			else { io.faces32[at] = v1i; io.faces32[at + 1] = v0i; io.faces32[at + 2] = third; }
-			if(isV) {
-				((uint4 *)io.pred)[x] = make_uint4(v1i, v0i, v2i, 0u);
-				const uint32_t b = nfront + nVb;
-				rg.stA(b, x, v1i, v0i);
-				rg.stB(b, nVb + 1u < nV ? b + 1u : (gend ? gid : CLERS_NOLINK), nVb ? b - 1u : next);
-				rg.stFl(b, 0u);
-			} else {
-				if(id >= eflush) rg.stFl(id, CLERS_DEL); else lead_g_set_flag(io.fl, id, CLERS_DEL);
-			}
-			if(tid == m - 1u) {
-				const uint32_t g0 = isL ? a : v0i, g1 = isV ? x : v1i, g2 = isV ? v1i : v0i;     // the gate after the run
-				sh.S.v0 = g0; sh.S.v1 = g1; sh.S.v2 = g2;
-				if(gend) {
-					rg.stA(gid, g0, g1, g2); rg.stB(gid, newprev, nextf); rg.stFl(gid, CLERS_NQ);
-					if(newprev >= eflush) rg.stB_next(newprev, gid); else clers_g_set_next(io.eb, newprev, gid);
-					if(nV == 0) { if(next >= eflush) rg.stB_prev(next, gid); else clers_g_set_prev(io.eb, next, gid); }
-					if(cm == C_DELAY) io.delayed[ndel] = gid;
+#pragma unroll
+		for(int h = 0; h < NH; h++) {
+			const uint32_t s = tid + (uint32_t)h*CT;
+			if((uint32_t)h*CT >= m) break;
+			if(s < m) {
+				const bool isV = (bV[h] >> lane) & 1u;
+				const bool prevIsV = lane ? ((bV[h] >> (lane - 1u)) & 1u) : psym[h] == (uint32_t)C_VERTEX;
+				const uint32_t v0i = nLb[h] ? sh.aL[nLb[h] - 1u] : s_v0;
+				const uint32_t v1i = nVb[h] ? vcount + nVb[h] - 1u : s_v1;
+				uint32_t v2i;
+				if(s == 0) v2i = s_v2;
+				else if(prevIsV) v2i = nVb[h] > 1u ? vcount + nVb[h] - 2u : s_v1;
+				else v2i = nLb[h] > 1u ? sh.aL[nLb[h] - 2u] : s_v0;
+				const uint32_t x = vcount + nVb[h];
+				const uint32_t third = isV ? x : a[h];
+				const size_t at = (size_t)(start + s)*3u;
+				if(io.faces16) { io.faces16[at] = (uint16_t)v1i; io.faces16[at + 1] = (uint16_t)v0i; io.faces16[at + 2] = (uint16_t)third; }
+				else { io.faces32[at] = v1i; io.faces32[at + 1] = v0i; io.faces32[at + 2] = third; }
+				if(isV) {
+					((uint4 *)io.pred)[x] = make_uint4(v1i, v0i, v2i, 0u);
+					const uint32_t b = nfront + nVb[h];
+					rg.stA(b, x, v1i, v0i);
+					rg.stB(b, nVb[h] + 1u < nV ? b + 1u : (gend ? gid : CLERS_NOLINK), nVb[h] ? b - 1u : next);
+					rg.stFl(b, 0u);
+				} else {
+					if(id[h] >= eflush) rg.stFl(id[h], CLERS_DEL); else lead_g_set_flag(io.fl, id[h], CLERS_DEL);
+				}
+				if(s == m - 1u) {
+					const uint32_t g0 = isV ? v0i : a[h], g1 = isV ? x : v1i, g2 = isV ? v1i : v0i;     // the gate after the run
+					sh.S.v0 = g0; sh.S.v1 = g1; sh.S.v2 = g2;
+					if(gend) {
+						rg.stA(gid, g0, g1, g2); rg.stB(gid, newprev, nextf); rg.stFl(gid, CLERS_NQ);
+						if(newprev >= eflush) rg.stB_next(newprev, gid); else clers_g_set_next(io.eb, newprev, gid);
+						if(nV == 0) { if(next >= eflush) rg.stB_prev(next, gid); else clers_g_set_prev(io.eb, next, gid); }
+						if(cm == C_DELAY) io.delayed[ndel] = gid;
+					}
 				}
 			}
 		}
@@ -236,39 +262,49 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 			sh.S.have = (!gend && start + m < end) ? 1u : 0u;
 			if(gend && cm == C_DELAY) sh.S.ndel = ndel + 1u;
 		}
-		cler += m; start += m; done += m;
+		cler += m + (gend ? 1u : 0u); start += m; done += m;
 		if(gend) { popnext = 1; break; }
-		if(m < (uint32_t)CT || start >= end || cler >= io.nclers) break;      // the run ended (or the group / the stream did)
-		if(nfront + nV + (uint32_t)CT + 1u > eflush + R) break;                // ring entries have to be written back first
+		if(m < WS || start >= end || cler >= io.nclers) break;                 // the run ended (or the group / the stream did)
+		if(nfront + nV + WS + 1u > eflush + R) break;                          // ring entries have to be written back first
 	}
 	if(tid == 0) { sh.tried = bail ? 1u : 0u; sh.windowed += done; }
 	return popnext;
 }
 
-// ---- CTA-wide pop of the implicit FIFO: 256 flag bytes per step -------------------------------------------------------------
+// ---- CTA-wide pop of the implicit FIFO: 1024 flag bytes per step -------------------------------------------------------------
 // The popped edge becomes the gate.  When the symbol waiting for it is BOUNDARY / DELAY (decoder.cpp:283, 327-331: the edge keeps
-// its record, nothing else changes) the symbol is consumed right here and the scan goes on from the next id.
-__device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t nseg, uint32_t &issued, uint32_t &ready) {
+// its record, nothing else changes) the symbol is consumed right here and the scan goes on from the next id.  Returns 1 when a
+// gate is loaded and a VERTEX / LEFT symbol is next (the caller goes straight to the window), else 0.
+template <int NH>
+__device__ int cta_pop(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, const uint32_t nseg, uint32_t &issued, uint32_t &ready, uint32_t &cler) {
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-	uint32_t scan = sh.S.scan, cler = sh.S.cler, ndel = sh.S.ndel;
+	uint32_t scan = sh.S.scan, ndel = sh.S.ndel;
 	const uint32_t nfront = sh.S.nfront, eflush = sh.S.eflush;
-	uint32_t found = CLERS_NOID, it = 0;
+	uint32_t found = CLERS_NOID, it = 0, c = 0xffu;
 	while(scan < nfront) {
-		const uint32_t id = scan + tid;
-		uint32_t fl = 0xffu;
-		if(id < nfront) fl = id >= eflush ? rg.ldFl(id) : lead_g_flag(io.fl, id);
-		const uint32_t alive = __ballot_sync(FULL, fl == 0u);
-		if(lane == 0) sh.wV[it][w] = alive;
+		// thread t looks at the four ids base + 4 t .. + 3 (one 32-bit load when they are in the ring)
+		const uint32_t base = scan & ~3u, id0 = base + 4u*tid;
+		uint32_t word = 0x01010101u;
+		if(id0 < nfront) {
+			if(id0 >= eflush) word = rg.ldFl4(id0);
+			else word = (uint32_t)io.fl[id0] | ((uint32_t)io.fl[id0 + 1] << 8) | ((uint32_t)io.fl[id0 + 2] << 16) | ((uint32_t)io.fl[id0 + 3] << 24);   // (store slots are padded)
+		}
+		uint32_t mine = CLERS_NOID;
+#pragma unroll
+		for(int k = 3; k >= 0; k--) { const uint32_t idk = id0 + (uint32_t)k; if(((word >> (8*k)) & 0xffu) == 0u && idk >= scan && idk < nfront) mine = idk; }
+		const uint32_t bal = __ballot_sync(FULL, mine != CLERS_NOID);
+		const uint32_t first = __shfl_sync(FULL, mine, bal ? (uint32_t)__ffs(bal) - 1u : 0u);
+		if(lane == 0) sh.wA[it][w] = bal ? first : CLERS_NOID;
 		__syncthreads();
 		found = CLERS_NOID;
 #pragma unroll
-		for(int j = CTW - 1; j >= 0; j--) { const uint32_t x = sh.wV[it][j]; if(x) found = scan + (uint32_t)j*32u + (uint32_t)__ffs(x) - 1u; }
+		for(int j = CTW - 1; j >= 0; j--) { const uint32_t x = sh.wA[it][j]; if(x != CLERS_NOID) found = x; }
 		it ^= 1u;
-		if(found == CLERS_NOID) { scan += CT; continue; }
+		if(found == CLERS_NOID) { scan = base + 4u*CT; continue; }
 		scan = found + 1u;
-		uint32_t c = 0xffu;
-		if(cler < io.nclers) { cta_symbols(io, rg, sh, cler, nseg, issued, ready, cler + 1u); c = rg.sym(cler); }
+		c = 0xffu;
+		if(cler < io.nclers) { cta_symbols(io, rg, sh.bar, cler, nseg, issued, ready, cler + 1u); c = rg.sym(cler); }
 		if(c == C_BOUNDARY || (c == C_DELAY && ndel < io.cap)) {
 			if(c == C_DELAY) { if(tid == 0) io.delayed[ndel] = found; ndel++; }
 			cler++;
@@ -281,19 +317,21 @@ __device__ void cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh, const ui
 		sh.S.scan = scan < nfront ? scan : nfront;
 		sh.S.cler = cler; sh.S.ndel = ndel;
 		if(found != CLERS_NOID) {
-			uint32_t p, q, a, b, c;
-			if(found >= eflush) { rg.ldB(found, p, q); rg.ldA(found, a, b, c); }
-			else { const uint2_t t_ = lead_g_load(io.eb, found); p = t_.x; q = t_.y; const uint4_t u_ = follow_g_load(io.ea, found); a = u_.x; b = u_.y; c = u_.z; }
-			sh.S.prev = p; sh.S.next = q; sh.S.v0 = a; sh.S.v1 = b; sh.S.v2 = c;
+			uint32_t p, q, a, b, c2;
+			if(found >= eflush) { rg.ldB(found, p, q); rg.ldA(found, a, b, c2); }
+			else { const uint2_t t_ = lead_g_load(io.eb, found); p = t_.x; q = t_.y; const uint4_t u_ = follow_g_load(io.ea, found); a = u_.x; b = u_.y; c2 = u_.z; }
+			sh.S.prev = p; sh.S.next = q; sh.S.v0 = a; sh.S.v1 = b; sh.S.v2 = c2;
 			sh.S.lp = sh.S.ln = 0; sh.S.have = 1; sh.S.cf = found;
 		}
 		sh.tried = 0;
 	}
+	return found != CLERS_NOID && c <= (uint32_t)C_LEFT;
 }
 
-__global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket, uint32_t R,
-                                                  uint32_t runmin) {
-	__shared__ CtaShared sh;
+template <int NH>
+__global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket, uint32_t R) {
+	constexpr uint32_t WS = NH*CT;
+	__shared__ CtaShared<NH> sh;
 	const uint32_t tid = threadIdx.x;
 	CtaRings rg;
 	{
@@ -302,10 +340,9 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		rg.aA = sbase; rg.aB = sbase + R*16u; rg.aX = rg.aB + R*8u; rg.aS = rg.aX + R;
 		rg.RM = R - 1u; rg.sq = 0;
 	}
-	(void)runmin;
 	if(tid == 0) for(uint32_t k = 0; k < CTA_NSEG; k++) mbar_init(&sh.bar[k], 1);
-	const uint32_t KEEP = R - 4u*(uint32_t)CT;             // ring entries kept after a write-back
-	const uint32_t ROOM = (uint32_t)CT + 4u;               // ids one step can allocate: a window (+ the gate's record), a start triangle
+	const uint32_t KEEP = R - 2u*WS;                       // ring entries kept after a write-back
+	const uint32_t ROOM = WS + 4u;                         // ids one step can allocate: a window (+ the gate's record), a start triangle
 	for(;;) {
 		__syncthreads();
 		if(tid == 0) sh.work = atomicAdd(ticket, 1u);
@@ -339,9 +376,10 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 			__syncthreads();                               // state, rings and outputs of the previous step are visible
 			mode = sh.mode;
 			if(mode) break;
-			const uint32_t cler = sh.S.cler, nfront = sh.S.nfront, eflush = sh.S.eflush;
+			uint32_t cler = sh.S.cler, start = sh.S.start;
+			const uint32_t nfront = sh.S.nfront, eflush = sh.S.eflush, end = sh.S.end;
 			if(nfront + ROOM > eflush + R) {               // write ring entries leaving the window back to the reach-back store
-				const uint32_t e1 = nfront - KEEP;
+				const uint32_t e1 = (nfront - KEEP) & ~3u;     // (a multiple of 4: the pop reads four flags per load)
 				for(uint32_t id = eflush + tid; id < e1; id += CT) {
 					uint32_t a, b, c, p, n;
 					rg.ldA(id, a, b, c); rg.ldB(id, p, n);
@@ -352,27 +390,38 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 				continue;
 			}
 			const uint32_t have = sh.S.have, tried = sh.tried;
-			const bool canpop = sh.S.start < sh.S.end && sh.S.scan < nfront;
-			cta_symbols(io, rg, sh, cler, nseg, issued, ready, min(io.nclers, cler + 2u));
+			const bool canpop = start < end && sh.S.scan < nfront;
+			cta_symbols(io, rg, sh.bar, cler, nseg, issued, ready, min(io.nclers, cler + 2u));
 			const uint32_t c0 = cler < io.nclers ? rg.sym(cler) : 0xffu;
-			if(have && !tried && c0 <= (uint32_t)C_LEFT) {
-				if(cta_window(io, rg, sh, R, nseg, issued, ready)) {
-					__syncthreads();                       // the flags this window set are visible to the scan
-					cta_pop(io, rg, sh, nseg, issued, ready);
+			int step = 2;                                  // 0 window, 1 pop, 2 one scalar symbol
+			if(have && !tried && c0 <= (uint32_t)C_LEFT) step = 0;
+			else if(!have && canpop) step = 1;
+			if(step == 2) {
+				if(tid == 0) {
+					// everything else, one symbol at a time: RIGHT, END, SPLIT, BOUNDARY / DELAY on a gate the window did not retire, start
+					// triangles, group changes, the delayed stack, and the symbol a window declined
+					const uint32_t c1 = sh.S.cler, s1 = sh.S.start, g1 = sh.S.g, h1 = sh.S.have, n1 = sh.S.ndel, q1 = sh.S.scan;
+					int rc = clers_merged(io, rg, sh.S, 1, false, 2u, splitbits);
+					if(rc == 0 && c1 == sh.S.cler && s1 == sh.S.start && g1 == sh.S.g && h1 == sh.S.have && n1 == sh.S.ndel && q1 == sh.S.scan) rc = -5;   // no progress
+					sh.tried = 0;
+					sh.mode = rc;
 				}
-			} else if(!have && canpop) cta_pop(io, rg, sh, nseg, issued, ready);
-			else if(tid == 0) {
-				// everything else, one symbol at a time: RIGHT, END, SPLIT, BOUNDARY / DELAY on a gate the window did not retire, start
-				// triangles, group changes, the delayed stack, and the symbol a window declined
-				const uint32_t c0 = sh.S.cler, s0 = sh.S.start, g0 = sh.S.g, h0 = sh.S.have, n0 = sh.S.ndel, q0 = sh.S.scan;
-				int rc = clers_merged(io, rg, sh.S, 1, false, 2u, splitbits);
-				if(rc == 0 && c0 == sh.S.cler && s0 == sh.S.start && g0 == sh.S.g && h0 == sh.S.have && n0 == sh.S.ndel && q0 == sh.S.scan) rc = -5;   // no progress
-				sh.tried = 0;
-				sh.mode = rc;
+				continue;
+			}
+			// strips: window(s) -> the gate retires on BOUNDARY / DELAY -> pop -> window(s) ... without passing through the dispatch above
+			for(;;) {
+				if(step == 0) {
+					if(!cta_window<NH>(io, rg, sh, R, nseg, issued, ready, cler, start, end)) break;
+					__syncthreads();                       // the flags and the state this window wrote are visible to the scan
+					step = 1;
+				} else {
+					if(!cta_pop<NH>(io, rg, sh, nseg, issued, ready, cler)) break;
+					step = 0;
+				}
 			}
 		}
 		// every copy that was issued has to land before the slots are reused by the next mesh
-		while(ready < issued) { const uint32_t q = rg.sq + ready; mbar_wait(&sh.bar[q & (CTA_NSEG - 1u)], (q >> 2) & 1u); ready++; }
+		while(ready < issued) { const uint32_t q = rg.sq + ready; mbar_wait(&sh.bar[q & (CTA_NSEG - 1u)], (q >> CTA_NSEG_LOG) & 1u); ready++; }
 		rg.sq += issued;
 		uint32_t vcount = sh.S.vcount;
 		const bool bad = mode < 0;
@@ -389,15 +438,24 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 }
 
 int launch_clers_cta(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, uint32_t runmin, cudaStream_t s) {
-	// ring size: as much shared memory per mesh as leaves every mesh of the batch resident (up to 8 CTAs of 256 threads per SM)
+	// ring size: as much shared memory per mesh as leaves every mesh of the batch resident (up to 4 CTAs of 256 threads per SM);
+	// windows of 1024 symbols where the ring is large enough to keep two of them plus a strip of reach-back, else 512
+	(void)runmin;
 	uint32_t R = 8192;
 	if(nwork > (uint32_t)sms) R = 4096;
 	if(nwork > 2u*(uint32_t)sms) R = 2048;
 	const size_t smem = (size_t)R*25u + CTA_NSEG*CTA_SEG;
-	cudaError_t e = cudaFuncSetAttribute(k_clers_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if(e != cudaSuccess) return (int)e;
 	const uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
-	k_clers_cta<<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R, runmin);
+	cudaError_t e;
+	if(R >= 4096) {
+		e = cudaFuncSetAttribute(k_clers_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return (int)e;
+		k_clers_cta<4><<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R);
+	} else {
+		e = cudaFuncSetAttribute(k_clers_cta<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e != cudaSuccess) return (int)e;
+		k_clers_cta<2><<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R);
+	}
 	e = cudaGetLastError();
 	return e == cudaSuccess ? 0 : (int)e;
 }
