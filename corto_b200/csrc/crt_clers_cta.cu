@@ -50,14 +50,15 @@ struct CtaRings {
 	__device__ __forceinline__ uint32_t ldFl(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aX + (id & RM))); return v; }
 	__device__ __forceinline__ uint32_t ldFl4(uint32_t id) const { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(aX + (id & RM))); return v; }   // id % 4 == 0
 	__device__ __forceinline__ void stFl(uint32_t id, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(aX + (id & RM)), "r"(v) : "memory"); }
-	__device__ __forceinline__ uint32_t sym(uint32_t i) const {
+	__device__ __forceinline__ uint32_t sym(uint32_t i) const {              // the segments are one contiguous 4 KB ring
 		uint32_t v;
-		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aS + (((sq + (i >> CTA_SEG_LOG)) & (CTA_NSEG - 1u)) << CTA_SEG_LOG) + (i & (CTA_SEG - 1u))));
+		asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(aS + (((sq << CTA_SEG_LOG) + i) & (CTA_NSEG*CTA_SEG - 1u))));
 		return v;
 	}
 };
 
-template <int NH> struct CtaShared {
+constexpr int NHMAX = 4;
+struct CtaShared {
 	MergedState S;
 	int32_t mode;                 // 0 running, 1 done, < 0 error
 	uint32_t tried;               // the last window attempt declined its first symbol: it goes the scalar way
@@ -65,18 +66,19 @@ template <int NH> struct CtaShared {
 	uint32_t windowed;            // symbols that went through the CTA-wide windows
 	uint32_t pk[2][32];           // per virtual warp of a window: first stop | V count << 8 | L count << 16 (counts before the stop)
 	uint32_t wA[2][CTW];          // pop: first alive id per warp
-	uint32_t aL[NH*CT + 1];       // prev-chain ids (slow path only), then the label v0 of the k-th edge the run's LEFTs consume
+	uint32_t aL[NHMAX*CT + 1];    // prev-chain ids (slow path only), then the label v0 of the k-th edge the run's LEFTs consume
 	uint32_t work;
 	alignas(8) uint64_t bar[CTA_NSEG];
 };
 
 // ---- symbol segments -----------------------------------------------------------------------------------------------------
 // Segment s of the current mesh (symbols [512 s, 512 s + 512)) is copy number sq + s of this CTA: slot (sq + s) & 7, and
-// the ((sq + s) >> 3)-th use of that slot's mbarrier.  Segments up to (cler >> 9) + 7 are in flight (the slot of segment s + 8
-// is free once the cursor has left segment s).  `issued` / `ready` are uniform counters every thread keeps in registers.
+// the ((sq + s) >> 3)-th use of that slot's mbarrier.  Segments up to (cler >> 9) + 6 are in flight (the slot of segment s + 8
+// is free once the cursor has left segment s + 1).  `issued` / `ready` are uniform counters every thread keeps in registers.
 __device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &rg, uint64_t *bar, uint32_t cler, uint32_t nseg, uint32_t &issued, uint32_t &ready,
                                             uint32_t upto /* symbols below this index must be readable */) {
-	const uint32_t want = min(nseg, (cler >> CTA_SEG_LOG) + CTA_NSEG);
+	// (one slot of slack: symbol cler - 1 — the BOUNDARY a window just retired — may still be read by a slow thread of the last step)
+	const uint32_t want = min(nseg, (cler >> CTA_SEG_LOG) + CTA_NSEG - 1u);
 	if(issued < want) {
 		if(threadIdx.x == 0) {
 			fence_proxy_async();
@@ -109,8 +111,8 @@ __device__ __forceinline__ void cta_symbols(const ClersIO &io, const CtaRings &r
 // symbol gives it a record (decoder.cpp:283, 327-331 — the edge stays in the front) and the caller goes straight to the FIFO
 // pop.  Returns 1 in that case, else 0.  cler / start: uniform cursors, updated.
 template <int NH>
-__device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready,
-                          uint32_t &cler, uint32_t &start, const uint32_t end) {
+__device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t R, const uint32_t nseg, uint32_t &issued, uint32_t &ready,
+                          uint32_t &cler, uint32_t &start, const uint32_t end, uint4 &popargs /* scan, ndel, nfront, eflush for the pop */) {
 	constexpr uint32_t WS = NH*CT, NVW = NH*CTW;
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
@@ -122,22 +124,21 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, co
 		const uint32_t lim = min(WS, min(io.nclers - cler, end - start));
 		cta_symbols(io, rg, sh.bar, cler, nseg, issued, ready, min(io.nclers, cler + lim + 1u));
 		// ---- phase A: classify my symbols, one packed word per virtual warp
-		uint32_t bV[NH], bL[NH], psym[NH];
+		uint32_t bV[NH], bL[NH];
 #pragma unroll
 		for(int h = 0; h < NH; h++) {
 			const uint32_t s = tid + (uint32_t)h*CT;
 			const uint32_t c = s < lim ? rg.sym(cler + s) : 0xffu;
-			psym[h] = (lane == 0 && s > 0 && s < lim) ? rg.sym(cler + s - 1u) : 0xffu;       // the symbol before my warp's first
 			bV[h] = __ballot_sync(FULL, c == C_VERTEX); bL[h] = __ballot_sync(FULL, c == C_LEFT);
 			const uint32_t stop = ~(bV[h] | bL[h]);
 			const uint32_t k = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
 			const uint32_t pm = stop ? (1u << k) - 1u : FULL;
-			if(lane == 0) sh.pk[it][w + (uint32_t)h*CTW] = k | ((uint32_t)__popc(bV[h] & pm) << 8) | ((uint32_t)__popc(bL[h] & pm) << 16);
+			if(lane == 0) sh.pk[it][w + (uint32_t)h*CTW] = k | ((uint32_t)__popc(bV[h] & pm) << 8) | ((uint32_t)__popc(bL[h] & pm) << 16) | ((bV[h] >> 31) << 24);
 		}
 		__syncthreads();                                   // B1 (also: state and rings written by the previous step are visible)
 		// ---- phase B: ranks
 		const uint32_t prev = sh.S.prev, next = sh.S.next, nfront = sh.S.nfront, vcount = sh.S.vcount, eflush = sh.S.eflush, ndel = sh.S.ndel;
-		const uint32_t s_v0 = sh.S.v0, s_v1 = sh.S.v1, s_v2 = sh.S.v2;
+		const uint32_t s_v0 = sh.S.v0, s_v1 = sh.S.v1, s_v2 = sh.S.v2, s_scan = sh.S.scan;
 		const uint32_t e = lane < NVW ? sh.pk[it][lane] : 32u;
 		const uint32_t stopb = __ballot_sync(FULL, (e & 0x3fu) < 32u);
 		const uint32_t ws = stopb ? (uint32_t)__ffs(stopb) - 1u : 32u;            // first virtual warp with a stop
@@ -153,12 +154,13 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, co
 		if(m > lim) m = lim;                               // (symbols past lim read 0xff: m <= lim already; belt and braces)
 		if(m < 1u || nfront + nV + 1u > io.cap || vcount + nV > io.nvert) { bail = done == 0; break; }
 		if(nfront + nV + 1u > eflush + R) break;           // the caller writes ring entries back first
-		uint32_t nVb[NH], nLb[NH], id[NH], a[NH];
+		uint32_t nVb[NH], nLb[NH], id[NH], a[NH], pV[NH];
 		// ---- prev chain, fast path: consecutive ids prev, prev + 1, ... (the queued edges of one earlier strip)
 		bool good = true;
 #pragma unroll
 		for(int h = 0; h < NH; h++) {
 			const uint32_t base = __shfl_sync(FULL, excl, w + (uint32_t)h*CTW);
+			pV[h] = (__shfl_sync(FULL, e, (w + (uint32_t)h*CTW - 1u) & 31u) >> 24) & 1u;     // was the last symbol of the virtual warp before mine a VERTEX
 			nVb[h] = (base & 0xffffu) + (uint32_t)__popc(bV[h] & below);
 			nLb[h] = (base >> 16) + (uint32_t)__popc(bL[h] & below);
 			id[h] = prev + nLb[h]; a[h] = 0;
@@ -217,7 +219,7 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, co
 			if((uint32_t)h*CT >= m) break;
 			if(s < m) {
 				const bool isV = (bV[h] >> lane) & 1u;
-				const bool prevIsV = lane ? ((bV[h] >> (lane - 1u)) & 1u) : psym[h] == (uint32_t)C_VERTEX;
+				const bool prevIsV = lane ? ((bV[h] >> (lane - 1u)) & 1u) : pV[h] != 0u;
 				const uint32_t v0i = nLb[h] ? sh.aL[nLb[h] - 1u] : s_v0;
 				const uint32_t v1i = nVb[h] ? vcount + nVb[h] - 1u : s_v1;
 				uint32_t v2i;
@@ -263,7 +265,7 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, co
 			if(gend && cm == C_DELAY) sh.S.ndel = ndel + 1u;
 		}
 		cler += m + (gend ? 1u : 0u); start += m; done += m;
-		if(gend) { popnext = 1; break; }
+		if(gend) { popnext = 1; popargs = make_uint4(s_scan, ndel + (cm == C_DELAY ? 1u : 0u), nfront + nV + 1u, eflush); break; }
 		if(m < WS || start >= end || cler >= io.nclers) break;                 // the run ended (or the group / the stream did)
 		if(nfront + nV + WS + 1u > eflush + R) break;                          // ring entries have to be written back first
 	}
@@ -275,14 +277,29 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, co
 // The popped edge becomes the gate.  When the symbol waiting for it is BOUNDARY / DELAY (decoder.cpp:283, 327-331: the edge keeps
 // its record, nothing else changes) the symbol is consumed right here and the scan goes on from the next id.  Returns 1 when a
 // gate is loaded and a VERTEX / LEFT symbol is next (the caller goes straight to the window), else 0.
-template <int NH>
-__device__ int cta_pop(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, const uint32_t nseg, uint32_t &issued, uint32_t &ready, uint32_t &cler) {
+// Nothing of the shared state is read here (scan, ndel, nfront, eflush come in registers): thread 0's writes at the end are
+// ordered against every other thread's reads by the barriers of the caller's next step.
+__device__ int cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uint32_t nseg, uint32_t &issued, uint32_t &ready, uint32_t &cler, const uint4 args) {
 	const uint32_t FULL = 0xffffffffu;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-	uint32_t scan = sh.S.scan, ndel = sh.S.ndel;
-	const uint32_t nfront = sh.S.nfront, eflush = sh.S.eflush;
+	uint32_t scan = args.x, ndel = args.y;
+	const uint32_t nfront = args.z, eflush = args.w;
 	uint32_t found = CLERS_NOID, it = 0, c = 0xffu;
 	while(scan < nfront) {
+		// the next queued edge is usually one of the first few ids: every thread reads the same eight flags (no barrier)
+		if(scan >= eflush) {
+			const uint32_t b0 = scan & ~3u;
+			const uint32_t w0 = rg.ldFl4(b0), w1 = rg.ldFl4(b0 + 4u);
+			uint32_t hit = CLERS_NOID;
+#pragma unroll
+			for(int k = 7; k >= 0; k--) {
+				const uint32_t idk = b0 + (uint32_t)k, f = ((k < 4 ? w0 : w1) >> (8*(k & 3))) & 0xffu;
+				if(f == 0u && idk >= scan && idk < nfront) hit = idk;
+			}
+			if(hit == CLERS_NOID && b0 + 8u >= nfront) { scan = nfront; break; }
+			found = hit;
+		}
+		if(found == CLERS_NOID) {
 		// thread t looks at the four ids base + 4 t .. + 3 (one 32-bit load when they are in the ring)
 		const uint32_t base = scan & ~3u, id0 = base + 4u*tid;
 		uint32_t word = 0x01010101u;
@@ -302,6 +319,7 @@ __device__ int cta_pop(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, const
 		for(int j = CTW - 1; j >= 0; j--) { const uint32_t x = sh.wA[it][j]; if(x != CLERS_NOID) found = x; }
 		it ^= 1u;
 		if(found == CLERS_NOID) { scan = base + 4u*CT; continue; }
+		}
 		scan = found + 1u;
 		c = 0xffu;
 		if(cler < io.nclers) { cta_symbols(io, rg, sh.bar, cler, nseg, issued, ready, cler + 1u); c = rg.sym(cler); }
@@ -328,10 +346,10 @@ __device__ int cta_pop(const ClersIO &io, CtaRings &rg, CtaShared<NH> &sh, const
 	return found != CLERS_NOID && c <= (uint32_t)C_LEFT;
 }
 
-template <int NH>
+template <int NHK>
 __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket, uint32_t R) {
-	constexpr uint32_t WS = NH*CT;
-	__shared__ CtaShared<NH> sh;
+	constexpr uint32_t WS = NHK*CT;
+	__shared__ CtaShared sh;
 	const uint32_t tid = threadIdx.x;
 	CtaRings rg;
 	{
@@ -369,7 +387,7 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		io.fl = (uint8_t *)io.order;                       // no FIFO is stored: the `order` scratch backs the flag ring
 		const int splitbits = ilog2_u32(io.nvert) + 1;
 		const uint32_t nseg = (io.nclers + CTA_SEG - 1u)/CTA_SEG;
-		uint32_t issued = 0, ready = 0;
+		uint32_t issued = 0, ready = 0, hint = WS;
 		if(tid == 0) { merged_init(sh.S); sh.mode = 0; sh.tried = 0; sh.windowed = 0; }
 		int mode;
 		for(;;) {
@@ -390,7 +408,9 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 				continue;
 			}
 			const uint32_t have = sh.S.have, tried = sh.tried;
-			const bool canpop = start < end && sh.S.scan < nfront;
+			uint4 popargs = make_uint4(sh.S.scan, sh.S.ndel, nfront, eflush);
+			const bool canpop = start < end && popargs.x < nfront;
+			__syncthreads();                               // every thread has read the state: thread 0 may change it from here on
 			cta_symbols(io, rg, sh.bar, cler, nseg, issued, ready, min(io.nclers, cler + 2u));
 			const uint32_t c0 = cler < io.nclers ? rg.sym(cler) : 0xffu;
 			int step = 2;                                  // 0 window, 1 pop, 2 one scalar symbol
@@ -411,11 +431,19 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 			// strips: window(s) -> the gate retires on BOUNDARY / DELAY -> pop -> window(s) ... without passing through the dispatch above
 			for(;;) {
 				if(step == 0) {
-					if(!cta_window<NH>(io, rg, sh, R, nseg, issued, ready, cler, start, end)) break;
+					// window width by the length of the last run: strips of a regular mesh change slowly, and a narrow window is fewer
+					// instructions per step
+					const uint32_t before = cler;
+					int r;
+					if(NHK >= 4 && hint > 2u*CT) r = cta_window<4>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
+					else if(NHK >= 2 && hint > (uint32_t)CT) r = cta_window<2>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
+					else r = cta_window<1>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
+					hint = cler - before;
+					if(!r) break;
 					__syncthreads();                       // the flags and the state this window wrote are visible to the scan
 					step = 1;
 				} else {
-					if(!cta_pop<NH>(io, rg, sh, nseg, issued, ready, cler)) break;
+					if(!cta_pop(io, rg, sh, nseg, issued, ready, cler, popargs)) break;
 					step = 0;
 				}
 			}
