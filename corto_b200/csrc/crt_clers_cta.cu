@@ -155,7 +155,8 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 		if(m < 1u || nfront + nV + 1u > io.cap || vcount + nV > io.nvert) { bail = done == 0; break; }
 		if(nfront + nV + 1u > eflush + R) break;           // the caller writes ring entries back first
 		uint32_t nVb[NH], nLb[NH], id[NH], a[NH], pV[NH];
-		// ---- prev chain, fast path: consecutive ids prev, prev + 1, ... (the queued edges of one earlier strip)
+		// ---- prev chain, fast path: consecutive ids prev, prev + 1, ... (the queued edges of one earlier strip; on a regular mesh
+		// the strip before the last one, i.e. ~2.3 strips of ids back)
 		bool good = true;
 #pragma unroll
 		for(int h = 0; h < NH; h++) {
@@ -165,11 +166,12 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 			nLb[h] = (base >> 16) + (uint32_t)__popc(bL[h] & below);
 			id[h] = prev + nLb[h]; a[h] = 0;
 			if(tid + (uint32_t)h*CT < m && ((bL[h] >> lane) & 1u)) {
-				bool g = id[h] >= eflush && id[h] < nfront && id[h] != next;
+				bool g = id[h] < nfront && id[h] != next;
 				if(g) {
 					uint32_t pk, pn;
-					rg.ldB(id[h], pk, pn);
-					a[h] = rg.ldA0(id[h]);
+					if(id[h] >= eflush) { rg.ldB(id[h], pk, pn); a[h] = rg.ldA0(id[h]); }
+					else { const EdgeB l_ = io.eb[id[h]]; pk = l_.prev; pn = l_.next; a[h] = io.ea[id[h]].v0; }   // reach-back store: a strip further back than the ring
+					(void)pn;
 					if(nLb[h] + 1u == nL) sh.newprev = pk; else g = pk == id[h] + 1u;
 					sh.aL[nLb[h]] = a[h];
 				}

@@ -9,18 +9,33 @@
 namespace crtb {
 
 namespace {
+// Byte cursor over a blob.  Three modes: direct (host blob), recording (host blob; every byte the walk READS — never the
+// payload it skips — is appended to a tape), replay (no blob: the reads are served from such a tape while `p` tracks the
+// position in the blob the tape came from).  The walk is a deterministic function of the bytes it reads, so a replay visits
+// the same positions and yields the same directory: that is how a rank that holds a blob only in DEVICE memory gets its
+// directory without copying the payload back (crt_walk_tape / crt_batch_create_device).
 struct Cur {
 	const uint8_t *b; uint32_t len; uint32_t p; bool bad;
+	std::vector<uint8_t> *rec = nullptr;          // recording
+	const uint8_t *tape = nullptr; uint32_t tape_len = 0, tape_p = 0;   // replay (b == nullptr)
 	bool need(uint64_t n) { if(bad || (uint64_t)p + n > len) { bad = true; return false; } return true; }
-	uint32_t u8() { if(!need(1)) return 0; return b[p++]; }
-	uint32_t u16() { if(!need(2)) return 0; uint32_t v = b[p] | (b[p + 1] << 8); p += 2; return v; }           // cstream.h:250-257
-	uint32_t u32() { if(!need(4)) return 0; uint32_t v = b[p] | (b[p + 1] << 8) | (b[p + 2] << 16) | ((uint32_t)b[p + 3] << 24); p += 4; return v; }  // :259-270
+	// the next n bytes at p (n <= 65535): pointer valid until the next call
+	const uint8_t *rd(uint32_t n) {
+		if(!need(n)) return nullptr;
+		const uint8_t *src;
+		if(b) { src = b + p; if(rec) rec->insert(rec->end(), src, src + n); }
+		else { if((uint64_t)tape_p + n > tape_len) { bad = true; return nullptr; } src = tape + tape_p; tape_p += n; }
+		p += n;
+		return src;
+	}
+	uint32_t u8() { const uint8_t *s = rd(1); return s ? s[0] : 0; }
+	uint32_t u16() { const uint8_t *s = rd(2); return s ? (uint32_t)(s[0] | (s[1] << 8)) : 0; }                 // cstream.h:250-257
+	uint32_t u32() { const uint8_t *s = rd(4); return s ? (s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24)) : 0; }  // :259-270
 	std::string str() {                                                                                       // :277-280: u16 length incl. NUL
 		uint32_t n = u16();
-		if(!need(n)) return std::string();
-		std::string s((const char *)b + p, strnlen((const char *)b + p, n));
-		p += n;
-		return s;
+		const uint8_t *s = rd(n);
+		if(!s) return std::string();
+		return std::string((const char *)s, strnlen((const char *)s, n));
 	}
 	void skip(uint64_t n) { if(need(n)) p += (uint32_t)n; }
 	bool bits(uint32_t &off, uint32_t &nwords) {                                                              // :283-291
@@ -60,9 +75,10 @@ int ParsedMesh::find(const char *name) const {
 }
 
 int parse_header(const uint8_t *blob, int len, ParsedMesh &m, std::string &err) {
-	if(!blob || len < 0) { err = "null blob"; return CRT_E_ARG; }
+	if((!blob && !m.tape) || len < 0) { err = "null blob"; return CRT_E_ARG; }
 	if((uintptr_t)blob & 3) { err = "Memory must be alignegned on 4 bytes."; return CRT_E_ALIGN; }      // decoder.cpp:43-44 (sic)
 	Cur c{blob, (uint32_t)len, 0, false};
+	c.rec = m.record; c.tape = m.tape; c.tape_len = m.tape_len;
 	uint32_t magic = c.u32();
 	if(c.bad || magic != 0x787A6300u) { err = "Not a crt file."; return CRT_E_MAGIC; }                    // decoder.cpp:48-52
 	m.blob = blob; m.len = (uint32_t)len;
@@ -102,7 +118,7 @@ int parse_header(const uint8_t *blob, int len, ParsedMesh &m, std::string &err) 
 	}
 	m.nvert = c.u32();
 	m.nface = c.u32();
-	m.body = c.p;
+	m.body = c.p; m.tape_body = c.tape_p;
 	if(c.bad) { err = "blob truncated inside the header"; return CRT_E_TRUNCATED; }
 	for(auto &a: m.attrs) {
 		int nc = a.codec == CODEC_NORMAL ? 2 : a.N;
@@ -113,6 +129,7 @@ int parse_header(const uint8_t *blob, int len, ParsedMesh &m, std::string &err) 
 
 int walk_directory(ParsedMesh &m, std::string &err) {
 	Cur c{m.blob, m.len, m.body, false};
+	c.rec = m.record; c.tape = m.tape; c.tape_len = m.tape_len; c.tape_p = m.tape_body;
 	m.group_ends.clear(); m.group_props.clear(); m.streams.clear();
 	uint32_t ngroups = c.u32();                                 // index_attribute.h:89-99
 	if(!c.bad && (uint64_t)ngroups*5 > m.len) { err = "corrupt group table"; return CRT_E_TRUNCATED; }

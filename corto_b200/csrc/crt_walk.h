@@ -49,6 +49,11 @@ struct ParsedMesh {
 	uint32_t split_off = 0, split_nwords = 0;
 	std::vector<AttrStreams> streams;  // one per attr
 	bool walked = false;
+	// walk tapes (crt_walk.cpp: Cur): `record` collects the bytes the two functions below read; with `tape` set and blob ==
+	// nullptr they read from the tape instead (the blob itself lives in device memory only)
+	std::vector<uint8_t> *record = nullptr;
+	const uint8_t *tape = nullptr;
+	uint32_t tape_len = 0, tape_body = 0;
 	int find(const char *name) const;
 };
 
