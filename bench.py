@@ -49,6 +49,10 @@ def parse():
     p.add_argument("--distinct", type=int, default=None, help="distinct seeds to encode (default: all)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-shard", action="store_true", help="skip the configs[3] scatter + sharded decode block")
+    p.add_argument("--no-secondary", action="store_true", help="skip the tarta / c5 / c3 secondary lines (N=1 only)")
+    p.add_argument("--shard-batch", type=int, default=4096, help="meshes of the configs[3] batch the ingest rank holds")
+    p.add_argument("--shard-distinct", type=int, default=256, help="distinct seeds encoded for it (the rest are repeats)")
     return p.parse_args()
 
 
@@ -138,6 +142,134 @@ def run_reference(args, rank, world, blobs):
         "cpu_baseline": {"value": val, "unit": "MVerts/s", "cores": threads if kind == "reference" else 1, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "MVerts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def run_shard(args, rank, world, local):
+    """BASELINE configs[3] as north_star words it: `--shard-batch` mixed meshes held by rank 0 (in its HBM) -> LPT plan from the
+    walk tapes -> ONE grouped NCCL send/recv into each rank's device arena -> every rank decodes its bin (directory rebuilt from
+    the tapes, no payload byte returns to a host).  Strong scaling: the batch is fixed, N grows.  Device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import corto_b200
+    from corto_b200 import dist as cd
+    from oracle import workloads
+    dev = torch.device("cuda", local)
+    ing = None
+    if rank == 0:
+        blobs = workloads.build("c4", args.shard_batch, seed0=1, distinct=min(args.shard_distinct, args.shard_batch))
+        ing = cd.Ingest(blobs, world, device=dev, pin=True)           # set-up: the batch sits in rank 0's HBM, bin after bin
+        del blobs
+    if world > 1:
+        got = cd.scatter_blobs(ing, src=0, device=dev)
+    else:
+        m = ing.meta()
+        got = dict(arena=ing.arena, tapes=[np.frombuffer(t, dtype=np.uint8) for t in m["tapes"]], lens=m["lens"], ids=m["ids"][0], meta=m)
+        got["tapes"] = [got["tapes"][i] for i in got["ids"]]; got["lens"] = [m["lens"][i] for i in got["ids"]]
+    bd = corto_b200.BatchDecoder.from_device(got["tapes"], got["lens"], got["arena"])
+    bd.allocate()
+    bd.upload()
+    bd.decode()
+    torch.cuda.synchronize()
+    rc, _ = bd.status()
+    assert rc == 0, "sharded decode failed: %s" % corto_b200.lib().crt_last_error()
+    steps, sc, de, tot = max(2, min(args.steps, 5)), [], [], []
+    for k in range(steps + 1):                                            # first pass = warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        if world > 1:
+            cd.scatter_blobs(ing, src=0, device=dev, meta=got["meta"], out=got["arena"])
+        e1.record()
+        bd.rewalk(); bd.decode()
+        e2.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e0.elapsed_time(e2)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if k:
+            sc.append(float(t[0])); de.append(float(t[1])); tot.append(float(t[2]))
+    rc, _ = bd.status()
+    assert rc == 0
+    # optional gather of one output arena (positions) to rank 0: bounded by rank 0's NVLink ingress, timed separately
+    gather_ms = None
+    if world > 1:
+        rows = [None] * world
+        dist.all_gather_object(rows, int(bd.total_verts))
+        g = cd.gather_rows(bd.out["position"], rows, dst=0)          # first pass: NCCL opens the reverse channels, the allocator grows
+        del g
+        dist.barrier(); torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        g = cd.gather_rows(bd.out["position"], rows, dst=0)
+        g1.record(); torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t[0])
+        del g
+    verts = torch.tensor([float(bd.total_verts)], device="cuda")
+    if world > 1:
+        dist.all_reduce(verts)
+    meta = got["meta"]
+    sent = sum(meta["slice_len"][1:]) if world > 1 else 0
+    ms = float(np.mean(tot))
+    return {"workload": "c4: %d mixed meshes 8K-256K verts, all attributes + groups (%d distinct seeds), held by rank 0, LPT-sharded" % (args.shard_batch, min(args.shard_distinct, args.shard_batch)),
+            "scaling": "strong", "n_gpus": world, "value": float(verts[0]) / (ms * 1e-3) / 1e6, "unit": "MVerts/s", "ms_per_step": ms,
+            "scatter_ms": float(np.mean(sc)), "decode_ms": float(np.mean(de)), "steps": steps,
+            "scatter_bytes": int(sent), "scatter_gbs": (sent / (np.mean(sc) * 1e-3) / 1e9) if sent else None,
+            "lpt_max_over_mean_load": meta["load_max_over_mean"], "gather_position_ms": gather_ms,
+            "exchange": "one torch.distributed.batch_isend_irecv (ncclGroupStart/End) from rank 0; tapes as metadata; no host bounce",
+            "limiter": "rank 0's NVLink egress for scatter_ms; the largest LPT bin's decode for decode_ms"}
+
+
+def run_secondary(args):
+    """N=1 only: the other BASELINE configs and the real scan, device-resident, a few steps each (driver-visible side lines)."""
+    import torch
+    import corto_b200
+    from oracle import workloads, refshim
+    out = {}
+    for w, batch, distinct in (("tarta", 64, 1), ("c5", 1, 1), ("c3", 512, 16)):
+        if w == "tarta" and not os.path.exists(refshim.TARTA):
+            continue
+        try:
+            blobs = workloads.build(w, batch, seed0=1, distinct=distinct)
+            bd = corto_b200.BatchDecoder(blobs)
+            bd.allocate(); bd.upload()
+            for _ in range(2):
+                bd.rewalk(); bd.decode()
+            torch.cuda.synchronize()
+            rc, _ = bd.status()
+            assert rc == 0
+            k = 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                bd.rewalk(); bd.decode()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / k
+            ib, ob = algorithmic_bytes(bd)
+            out[w] = {"workload": workloads.DESCRIPTION[w], "batch": batch, "value": bd.total_verts / (ms * 1e-3) / 1e6, "unit": "MVerts/s",
+                      "ms_per_step": ms, "step_achieved_gbs": (ib + ob) / (ms * 1e-3) / 1e9}
+            del bd, blobs
+            torch.cuda.empty_cache()
+        except Exception as e:                                            # a side line must never take the headline down
+            out[w] = {"error": str(e)[:200]}
+    # configs[0]: ONE 34K-vertex mesh through the crt::Decoder-shaped call with host buffers (latency, not throughput)
+    try:
+        blob = workloads.build("c1", 1)[0]
+        d = corto_b200.Decoder(blob); d.decode()
+        ts = []
+        for _ in range(5):
+            d = corto_b200.Decoder(blob)
+            t0 = time.perf_counter(); d.decode(); ts.append(time.perf_counter() - t0)
+        lat = {"workload": workloads.DESCRIPTION["c1"], "ours_ms": 1e3 * min(ts)}
+        if refshim.available():
+            lat["reference_1thread_ms"] = 1e3 * refshim.decode_bench([blob], 1, 5)
+        out["c1_latency"] = lat
+    except Exception as e:
+        out["c1_latency"] = {"error": str(e)[:200]}
+    return out
 
 
 def WORKLOAD_NAME(args):
@@ -249,6 +381,7 @@ def main():
                 "stage_ms_from": "a re-run of the same steps right after the timed region with the library's stage timers (CUDA events) on",
                 "note": "mesh decode is bound by the serial CLERS automaton (instruction latency, not HBM); see DESIGN.md section 5"}
     launches = bd.launches * args.steps
+    verts_per_gpu, faces_per_gpu = int(bd.total_verts), int(bd.total_faces)
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------------
     e2e = None
@@ -287,8 +420,35 @@ def main():
         assert rc2 == 0
         e2e = {"value": total_verts * ke / (float(ems.item()) * 1e-3) / 1e6, "unit": "MVerts/s", "h2d_bytes_per_step": int(in_bytes),
                "d2h_bytes_per_step": int(d2h), "steps": ke, "pipelining": "2 batches in flight on 2 streams; wall clock over a full device sync"}
+        # the host ceiling beside it: a plain device -> pinned-host copy of one output arena set, nothing else running
+        big = max(host_out[0].values(), key=lambda t: t.numel() * t.element_size())
+        src = bds[0].out[[k for k, v in host_out[0].items() if v is big][0]]
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            big.copy_(src, non_blocking=True)
+        c1.record(); torch.cuda.synchronize()
+        d2h_gbs = 3 * big.numel() * big.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        e2e["d2h_pinned_gbs"] = d2h_gbs
+        e2e["d2h_bound_mverts_s"] = world * d2h_gbs * 1e9 / (d2h / max(bds[0].total_verts, 1)) / 1e6   # if the step were nothing but its D2H
 
     clocks = sampler.stop()          # sampled across both timed regions (device-resident and end-to-end)
+
+    # ---- configs[3]: scatter over NVLink + sharded decode (strong scaling), and the side lines ---------------------------
+    del bd
+    if not args.no_e2e:
+        del bd2, bds, host_out
+    torch.cuda.empty_cache()
+    shard = None
+    if not args.no_shard:
+        try:
+            shard = run_shard(args, rank, world, local)
+        except Exception as e:
+            shard = {"error": str(e)[:300]}
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = run_secondary(args)
 
     # ---- CPU baseline beside it (rank 0, N=1) -----------------------------------------------------------------------
     cpu = None
@@ -311,13 +471,13 @@ def main():
             "metric": "decoded MVerts/s (batched .crt)", "value": value, "unit": "MVerts/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+fp32", "data": "synthetic" if refshim.available() else "synthetic (one pre-encoded blob replicated: reference encoder not built here)",
-            "config": {"workload": WORKLOAD_NAME(args), "batch_per_gpu": batch, "verts_per_gpu": int(bd.total_verts),
-                       "faces_per_gpu": int(bd.total_faces), "blob_bytes_per_gpu": int(in_bytes), "output_bytes_per_gpu": int(out_bytes),
+            "config": {"workload": WORKLOAD_NAME(args), "batch_per_gpu": batch, "verts_per_gpu": verts_per_gpu,
+                       "faces_per_gpu": faces_per_gpu, "blob_bytes_per_gpu": int(in_bytes), "output_bytes_per_gpu": int(out_bytes),
                        "parallelism": "mesh-sharded x%d, no data-path collective" % world,
                        "l2": "inputs+outputs (%.2f GB) larger than the 126 MB L2; no explicit flush" % ((in_bytes + out_bytes) / 1e9),
                        "timed_region": "host directory walk + H2D directory + all decode kernels"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "wall_s": t_wall}))
+            "shard": shard, "secondary": secondary, "wall_s": t_wall}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -80,6 +80,9 @@ def lib():
         L.crt_batch_debug_clers.argtypes = [vp, ci, vp, cu32, C.POINTER(cu32)]
         L.crt_batch_debug_prediction.argtypes = [vp, ci, vp]
         L.crt_shard_lpt.argtypes = [ci, vp, vp, vp, ci, vp]
+        L.crt_walk_tape.argtypes = [vp, ci, vp, ci, C.POINTER(cu32), C.POINTER(cu32), C.POINTER(cu32)]
+        L.crt_batch_create_device.restype = vp; L.crt_batch_create_device.argtypes = [ci, vp, vp, vp, vp]
+        L.crt_batch_directory_signature.restype = cu64; L.crt_batch_directory_signature.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -218,14 +221,25 @@ class BatchDecoder:
     """Batched, device-resident decode (include/corto_b200.h group 3).  Outputs are torch CUDA tensors laid out as
     flat arenas, meshes concatenated in batch order; ``vert_base`` / ``face_base`` locate mesh i."""
 
-    def __init__(self, blobs, normals16=False, index16=False, color_components=4, bind=None, device=None):
+    def __init__(self, blobs, normals16=False, index16=False, color_components=4, bind=None, device=None, _device_arena=None):
         import torch
         self.torch = torch
-        self._blobs = [_aligned_copy(b) for b in blobs]
-        n = len(self._blobs)
-        ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in self._blobs])
-        lens = (C.c_int * max(n, 1))(*[len(b) for b in self._blobs])
-        self._h = lib().crt_batch_create(n, ptrs, lens)
+        if _device_arena is None:
+            self._blobs = [_aligned_copy(b) for b in blobs]
+            n = len(self._blobs)
+            ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in self._blobs])
+            lens = (C.c_int * max(n, 1))(*[len(b) for b in self._blobs])
+            self._h = lib().crt_batch_create(n, ptrs, lens)
+        else:
+            # blobs = (tapes, blob lengths): the payload is in `_device_arena` (a CUDA uint8 tensor) already
+            tapes, blob_lens = blobs
+            self._arena = _device_arena
+            self._tapes = [np.ascontiguousarray(t, dtype=np.uint8) for t in tapes]
+            n = len(self._tapes)
+            ptrs = (C.c_void_p * max(n, 1))(*[t.ctypes.data for t in self._tapes])
+            tl = (C.c_int * max(n, 1))(*[len(t) for t in self._tapes])
+            bl = (C.c_int * max(n, 1))(*[int(x) for x in blob_lens])
+            self._h = lib().crt_batch_create_device(n, ptrs, tl, bl, C.c_void_p(_device_arena.data_ptr()))
         if not self._h:
             raise CortoError(-1, lib().crt_last_error().decode())
         self.n = n
@@ -247,6 +261,13 @@ class BatchDecoder:
         self.out = {}
         self._want = bind
         self.launches = 0
+
+    @classmethod
+    def from_device(cls, tapes, blob_lens, arena, **kw):
+        """Batch over blobs that are ALREADY in device memory: `arena` is a CUDA uint8 tensor holding them back to back (each at
+        the sum of the 16-byte-rounded lengths before it), `tapes` their walk tapes (`walk_tape` on the rank that had the host
+        copy).  The arena is borrowed; no payload byte returns to the host (include/corto_b200.h: crt_batch_create_device)."""
+        return cls((tapes, blob_lens), _device_arena=arena, **kw)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -335,6 +356,20 @@ class BatchDecoder:
                 a = a.view(np.uint16 if self.index16 else np.uint32)
             res[k] = a
         return res
+
+
+def walk_tape(blob):
+    """(tape, nvert, nface, nattr) of one HOST blob: the bytes the header parse + directory walk read (no payload)."""
+    b = _aligned_copy(blob)
+    nv, nf, na = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    buf = np.empty(4096, dtype=np.uint8)
+    n = lib().crt_walk_tape(b.ctypes.data_as(C.c_void_p), len(b), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(nv), C.byref(nf), C.byref(na))
+    if n < 0:
+        raise CortoError(n, lib().crt_last_error().decode(errors="replace"))
+    if n > buf.size:
+        buf = np.empty(n, dtype=np.uint8)
+        n = lib().crt_walk_tape(b.ctypes.data_as(C.c_void_p), len(b), buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(nv), C.byref(nf), C.byref(na))
+    return buf[:n].copy(), nv.value, nf.value, na.value
 
 
 def shard_lpt(nvert, nface, nattr, world):

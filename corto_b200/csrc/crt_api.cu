@@ -63,6 +63,8 @@ struct crt_batch {
 	// device
 	int device = 0, sms = 148;
 	uint8_t *d_blobs = nullptr;        size_t blobs_bytes = 0;
+	std::vector<std::vector<uint8_t>> tapes;   // crt_batch_create_device: the walk tapes (the directory is re-walked from them)
+	bool blobs_external = false;       // crt_batch_create_device: d_blobs is the caller's arena (not owned, never copied into)
 	uint8_t *d_tables = nullptr;       size_t tables_bytes = 0;     // MeshDesc | TunDesc | groups | tiles ... (one H2D)
 	std::vector<uint8_t> h_tables;
 	uint8_t *d_scratch = nullptr;      size_t scratch_bytes = 0;    // symbols, per-mesh work, dictionaries, CLERS slots
@@ -107,12 +109,57 @@ extern "C" crt_batch *crt_batch_create(int n, const unsigned char *const *blobs,
 	return b;
 }
 
+// The bytes parse_header + walk_directory read from one blob (header, group table, block headers — a few hundred bytes, no
+// payload), in reading order.  Returns the tape length (the tape is written only when it fits `cap`), or a CRT_E_* code.
+extern "C" int crt_walk_tape(const unsigned char *blob, int len, unsigned char *tape, int cap, uint32_t *nvert, uint32_t *nface, uint32_t *nattr) {
+	ParsedMesh pm;
+	std::vector<uint8_t> rec;
+	pm.record = &rec;
+	std::string err;
+	int rc = parse_header(blob, len, pm, err);
+	if(rc == CRT_OK) rc = walk_directory(pm, err);
+	if(rc != CRT_OK) return fail(rc, err);
+	if(nvert) *nvert = pm.nvert;
+	if(nface) *nface = pm.nface;
+	if(nattr) *nattr = (uint32_t)pm.attrs.size();
+	if(tape && (int)rec.size() <= cap && !rec.empty()) memcpy(tape, rec.data(), rec.size());
+	return (int)rec.size();
+}
+
+// A batch whose blobs are ALREADY in device memory (e.g. received over NVLink from the rank that ingested them): `arena` holds
+// them back to back, blob i at the sum of the 16-byte-rounded lengths before it; the directory of each comes from its walk
+// tape (crt_walk_tape on the rank that had the host copy).  The arena is borrowed for the lifetime of the batch; nothing is
+// copied to or from the host but the tables.
+extern "C" crt_batch *crt_batch_create_device(int n, const unsigned char *const *tapes, const int *tape_lens, const int *blob_lens, const void *arena) {
+	if(n < 0 || (n > 0 && (!tapes || !tape_lens || !blob_lens || !arena)) || ((uintptr_t)arena & 15)) { fail(CRT_E_ARG, "bad arguments"); return nullptr; }
+	crt_batch *b = new crt_batch();
+	b->meshes.resize(n);
+	b->tapes.reserve(n);
+	b->vert_base.assign(n + 1, 0); b->face_base.assign(n + 1, 0);
+	for(int i = 0; i < n; i++) {
+		std::string err;
+		ParsedMesh &pm = b->meshes[i];
+		b->tapes.emplace_back(tapes[i], tapes[i] + (tape_lens[i] > 0 ? tape_lens[i] : 0));
+		pm.tape = b->tapes.back().data(); pm.tape_len = (uint32_t)b->tapes.back().size();
+		int rc = parse_header(nullptr, blob_lens[i], pm, err);
+		if(rc == CRT_OK) rc = walk_directory(pm, err);
+		if(rc != CRT_OK) { fail(rc, "blob " + std::to_string(i) + ": " + err); delete b; return nullptr; }
+		b->vert_base[i + 1] = b->vert_base[i] + pm.nvert;
+		b->face_base[i + 1] = b->face_base[i] + pm.nface;
+		b->total_bytes += (uint64_t)blob_lens[i];
+	}
+	b->d_blobs = (uint8_t *)arena;
+	b->blobs_external = true;
+	return b;
+}
+
 static void batch_free_device(crt_batch *b) {
-	if(b->d_blobs) cudaFree(b->d_blobs);
+	if(b->d_blobs && !b->blobs_external) cudaFree(b->d_blobs);
 	if(b->d_tables) cudaFree(b->d_tables);
 	if(b->d_scratch) cudaFree(b->d_scratch);
 	if(b->d_zero) cudaFree(b->d_zero);
-	b->d_blobs = b->d_tables = b->d_scratch = b->d_zero = nullptr;
+	if(!b->blobs_external) b->d_blobs = nullptr;
+	b->d_tables = b->d_scratch = b->d_zero = nullptr;
 	for(auto &s: b->stages) cudaEventDestroy(s.ev);
 	b->stages.clear();
 	for(int k = 0; k < 1; k++) {
@@ -363,15 +410,22 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	// ---- blob arena ----
 	uint64_t blobs_bytes = 16;
 	for(auto &m: b->meshes) blobs_bytes += align_up(m.len, 16);
-	if(!b->d_blobs || b->blobs_bytes < blobs_bytes) {
+	if(b->blobs_external) copy_blobs = false;
+	else if(!b->d_blobs || b->blobs_bytes < blobs_bytes) {
 		if(b->d_blobs) { cudaFree(b->d_blobs); b->d_blobs = nullptr; }
 		CU(cudaMalloc(&b->d_blobs, blobs_bytes));
 		b->blobs_bytes = blobs_bytes;
 		copy_blobs = true;
 	}
-	if(copy_blobs)
-		for(int i = 0; i < n; i++)
+	if(copy_blobs && n) {
+		// host blobs that already sit in one buffer with the arena's layout (16-byte-rounded, back to back) travel as ONE copy
+		bool contiguous = true;
+		for(int i = 1; i < n && contiguous; i++)
+			contiguous = b->meshes[i].blob == b->meshes[0].blob + b->h_mesh[i].blob_off;
+		if(contiguous) CU(cudaMemcpyAsync(b->d_blobs, b->meshes[0].blob, b->h_mesh[n - 1].blob_off + b->meshes[n - 1].len, cudaMemcpyHostToDevice, stream));
+		else for(int i = 0; i < n; i++)
 			CU(cudaMemcpyAsync(b->d_blobs + b->h_mesh[i].blob_off, b->meshes[i].blob, b->meshes[i].len, cudaMemcpyHostToDevice, stream));
+	}
 
 	// ---- scratch arena: symbols | per-mesh work | adj | dictionaries | CLERS slots ----
 	const uint64_t ntun = b->h_tun.size();
@@ -505,6 +559,9 @@ static uint64_t directory_signature(const crt_batch *b) {
 	for(auto &kv: b->binds) { for(char c: kv.first) mix((uint64_t)c); mix((uint64_t)kv.second.ptr); mix((uint64_t)kv.second.format); mix((uint64_t)kv.second.components); }
 	return h;
 }
+
+// (tests: a batch built from walk tapes must carry the same directory as one built from the host blobs)
+extern "C" uint64_t crt_batch_directory_signature(const crt_batch *b) { return directory_signature(b); }
 
 extern "C" int crt_batch_rewalk(crt_batch *b, void *stream) {
 	if(!b->uploaded) return fail(CRT_E_ARG, "crt_batch_rewalk before crt_batch_upload");

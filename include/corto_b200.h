@@ -134,6 +134,17 @@ enum { CRT_HAS_POSITION = 1, CRT_HAS_NORMAL = 2, CRT_HAS_COLOR = 4, CRT_HAS_UV =
 crt_batch *crt_batch_create(int n, const unsigned char *const *blobs, const int *lens);
 void crt_batch_destroy(crt_batch *b);
 
+/* Multi-GPU ingest: the rank that holds a blob in HOST memory records the few hundred bytes the header
+ * parse and the directory walk read from it (crt_walk_tape: no payload byte, returns the tape length or a CRT_E_* code; the
+ * tape is written when it fits `cap`; nvert / nface / nattr feed crt_shard_lpt); the rank that receives the blob in DEVICE
+ * memory builds its batch from the tapes and the arena the blobs arrived in (blob i at the sum of the 16-byte-rounded lengths
+ * before it, arena 16-byte aligned, borrowed while the batch lives).  No payload ever returns to a host. */
+int crt_walk_tape(const unsigned char *blob, int len, unsigned char *tape, int cap, uint32_t *nvert, uint32_t *nface, uint32_t *nattr);
+crt_batch *crt_batch_create_device(int n, const unsigned char *const *tapes, const int *tape_lens, const int *blob_lens, const void *arena);
+/* FNV-1a over every offset / size of the walked directory (and the bindings): equal for a batch built from host blobs and one
+ * built from their tapes. */
+uint64_t crt_batch_directory_signature(const crt_batch *b);
+
 int crt_batch_count(const crt_batch *b);
 int crt_batch_mesh_info(const crt_batch *b, int i, uint32_t *nvert, uint32_t *nface, uint32_t *attr_mask);
 /* Component count the headers give attribute `name` (0 = no mesh of the batch carries it): an arena bound under that name

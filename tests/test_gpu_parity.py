@@ -3,6 +3,9 @@
 `-m gpu`.  Ground truth = oracle/liboracle.so (pinned to the reference by tests/test_oracle.py) and, when the prebuilt
 reference shim travelled with the snapshot, the unmodified reference itself.
 """
+import glob
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +14,7 @@ from tests import cases
 from oracle import pyoracle, refshim
 
 pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _same(name, a, b):
@@ -51,6 +55,39 @@ def test_medium(name, builder):
     if not refshim.available():
         pytest.skip("needs the reference shim to encode")
     _check_blob(builder(), name)
+
+
+def test_batch_from_device_arena():
+    """crt_batch_create_device: the blobs exist in DEVICE memory only (one arena, as they arrive from the ingest rank over NVLink),
+    the directory comes from their walk tapes; decode, re-walk + decode again — every array equals the oracle's."""
+    import torch
+    blobs = [np.frombuffer(open(p, "rb").read(), dtype=np.uint8) for p in sorted(glob.glob(os.path.join(GOLDEN, "*.crt")))]
+    blobs = [b for b in blobs if not [a for a in pyoracle.info(corto_b200._aligned_copy(b))["attrs"] if a["name"] == "radius"]]
+    assert len(blobs) > 20
+    tapes = [corto_b200.walk_tape(b)[0] for b in blobs]
+    lens = [len(b) for b in blobs]
+    host = np.zeros(sum((n + 15) // 16 * 16 for n in lens) + 16, dtype=np.uint8)
+    o = 0
+    for b in blobs:
+        host[o:o + len(b)] = b
+        o += (len(b) + 15) // 16 * 16
+    arena = torch.from_numpy(host).cuda()
+    del host
+    bd = corto_b200.BatchDecoder.from_device(tapes, lens, arena, color_components=4)
+    bd.allocate(fill=0xA5)
+    bd.upload()
+    for _ in range(2):
+        bd.decode()
+        torch.cuda.synchronize()
+        rc, st = bd.status()
+        assert rc == 0, st
+        for i, blob in enumerate(blobs):
+            want = pyoracle.decode(corto_b200._aligned_copy(blob), color_out=4)
+            got = bd.mesh_outputs(i)
+            for k, w in want.items():
+                if isinstance(w, np.ndarray):
+                    _same("device-arena[%d]/%s" % (i, k), got[k], w)
+        bd.rewalk()
 
 
 def test_batch_mixed():

@@ -283,29 +283,84 @@ def test_shard_lpt_balances():
         assert load.max() / load.mean() < 1.02
 
 
+def test_walk_tapes_rebuild_the_directory():
+    """crt_walk_tape + crt_batch_create_device: the directory rebuilt from the tapes (no blob byte available) is the one the host
+    walk finds, for every fixture; a truncated tape is rejected."""
+    import glob
+    L = corto_b200.lib()
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "*.crt")))
+    blobs = [np.frombuffer(open(p, "rb").read(), dtype=np.uint8) for p in paths]
+    al = [corto_b200._aligned_copy(b) for b in blobs]
+    n = len(al)
+    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in al])
+    lens = (C.c_int * n)(*[len(b) for b in al])
+    h0 = L.crt_batch_create(n, ptrs, lens)
+    assert h0
+    tapes = [corto_b200.walk_tape(b)[0] for b in blobs]
+    assert max(len(t) for t in tapes) < 2048          # header + group table + block headers, never payload
+    tp = (C.c_void_p * n)(*[t.ctypes.data for t in tapes])
+    tl = (C.c_int * n)(*[len(t) for t in tapes])
+    fake_arena = C.c_void_p(1 << 20)                 # never dereferenced by create (16-byte aligned device address stand-in)
+    h1 = L.crt_batch_create_device(n, tp, tl, lens, fake_arena)
+    assert h1, L.crt_last_error()
+    assert L.crt_batch_directory_signature(h0) == L.crt_batch_directory_signature(h1)
+    assert L.crt_batch_total_verts(h0) == L.crt_batch_total_verts(h1) and L.crt_batch_total_faces(h0) == L.crt_batch_total_faces(h1)
+    L.crt_batch_destroy(h1)
+    # a tape cut short: the replay must fail cleanly
+    short = tapes[3][:len(tapes[3]) // 2].copy()
+    tp2 = (C.c_void_p * 1)(short.ctypes.data)
+    assert not L.crt_batch_create_device(1, tp2, (C.c_int * 1)(len(short)), (C.c_int * 1)(len(al[3])), fake_arena)
+    L.crt_batch_destroy(h0)
+
+
 def test_scatter_two_ranks_gloo(tmp_path):
-    """corto_b200.dist.scatter_blobs: rank 0 holds the blobs, LPT-shards them, every rank receives exactly its bin."""
+    """corto_b200.dist: rank 0 holds the blobs, LPT-shards them from their walk tapes, ONE grouped send/recv delivers every rank's
+    bin as a contiguous arena; each rank rebuilds its directory from the tapes (crt_batch_create_device)."""
     script = tmp_path / "w.py"
     script.write_text('''
-import os, sys, glob, hashlib
+import os, sys, glob, hashlib, ctypes as C
 sys.path.insert(0, %r)
 import numpy as np, torch, torch.distributed as dist
+import corto_b200
 from corto_b200 import dist as cd
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 paths = sorted(glob.glob(os.path.join(%r, "*.crt")))
-blobs = [np.frombuffer(open(p, "rb").read(), dtype=np.uint8) for p in paths] if rank == 0 else None
-mine, ids = cd.scatter_blobs(blobs, src=0, device="cpu")
+ing = None
+if rank == 0:
+    blobs = [np.frombuffer(open(p, "rb").read(), dtype=np.uint8) for p in paths]
+    ing = cd.Ingest(blobs, world, device="cpu")
+    assert 1.0 <= ing.load_max_over_mean < 1.5
+got = cd.scatter_blobs(ing, src=0, device="cpu")
+ids, lens, tapes, arena = got["ids"], got["lens"], got["tapes"], got["arena"].numpy()
 all_ids = [None] * world
 dist.all_gather_object(all_ids, ids)
 flat = sorted(i for x in all_ids for i in x)
 assert flat == list(range(len(paths))), flat
-for b, i in zip(mine, ids):
-    assert hashlib.sha1(b.tobytes()).hexdigest() == hashlib.sha1(open(paths[i], "rb").read()).hexdigest()
-assert len(mine) > 0
+o = 0
+for i, n in zip(ids, lens):
+    assert hashlib.sha1(arena[o:o + n].tobytes()).hexdigest() == hashlib.sha1(open(paths[i], "rb").read()).hexdigest()
+    assert o %% 16 == 0
+    o += (n + 15) // 16 * 16
+assert len(ids) > 0
+# the directory from the tapes == the directory from the bytes that arrived
+L = corto_b200.lib()
+n = len(ids)
+tp = (C.c_void_p * n)(*[t.ctypes.data for t in tapes]); tl = (C.c_int * n)(*[len(t) for t in tapes]); bl = (C.c_int * n)(*lens)
+h1 = L.crt_batch_create_device(n, tp, tl, bl, C.c_void_p(1 << 20))
+assert h1, L.crt_last_error()
+local = [corto_b200._aligned_copy(np.frombuffer(open(paths[i], "rb").read(), dtype=np.uint8)) for i in ids]
+h0 = L.crt_batch_create(n, (C.c_void_p * n)(*[b.ctypes.data for b in local]), bl)
+assert L.crt_batch_directory_signature(h0) == L.crt_batch_directory_signature(h1)
+# gather_rows: every rank contributes rank+1 rows
+rows = [r + 1 for r in range(world)]
+x = torch.full((rows[rank], 3), float(rank))
+g = cd.gather_rows(x, rows, dst=0)
+if rank == 0:
+    assert g.shape == (sum(rows), 3) and float(g[-1, 0]) == world - 1 and float(g[0, 0]) == 0.0
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok", len(mine))
+print("rank", rank, "ok", n)
 ''' % (ROOT, GOLDEN))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
