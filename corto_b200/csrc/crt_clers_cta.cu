@@ -349,7 +349,7 @@ __device__ int cta_pop(const ClersIO &io, CtaRings &rg, CtaShared &sh, const uin
 }
 
 template <int NHK>
-__global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket, uint32_t R) {
+__global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket, uint32_t R, bool defer) {
 	constexpr uint32_t WS = NHK*CT;
 	__shared__ CtaShared sh;
 	const uint32_t tid = threadIdx.x;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		rg.aA = sbase; rg.aB = sbase + R*16u; rg.aX = rg.aB + R*8u; rg.aS = rg.aX + R;
 		rg.RM = R - 1u; rg.sq = 0;
 	}
-	if(tid == 0) for(uint32_t k = 0; k < CTA_NSEG; k++) mbar_init(&sh.bar[k], 1);
+	if(tid == 0) { for(uint32_t k = 0; k < CTA_NSEG; k++) mbar_init(&sh.bar[k], 1); sh.flag = 0; }
 	const uint32_t KEEP = R - 2u*WS;                       // ring entries kept after a write-back
 	const uint32_t ROOM = WS + 4u;                         // ids one step can allocate: a window (+ the gate's record), a start triangle
 	for(;;) {
@@ -390,6 +390,26 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		const int splitbits = ilog2_u32(io.nvert) + 1;
 		const uint32_t nseg = (io.nclers + CTA_SEG - 1u)/CTA_SEG;
 		uint32_t issued = 0, ready = 0, hint = WS;
+		// Irregular meshes (real scans: runs of ~6 symbols between RIGHT / DELAY / BOUNDARY) gain nothing from CTA-wide windows and
+		// pay for the barriers: a sample of the stream decides, and such a mesh is left to the leader / follower kernel that
+		// launch_clers_cta starts right after this one (B.regular[mi] bit 31 = "deferred").
+		if(defer) {
+			const uint32_t ns = min(io.nclers, 16384u) & ~15u;
+			uint32_t other = 0;
+			for(uint32_t i = tid*16u; i < ns; i += CT*16u) {
+				const uint4 q = *(const uint4 *)(io.clers + i);
+				const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+				for(int k = 0; k < 4; k++) other += (uint32_t)__popc((ws[k] | (ws[k] >> 1)) & 0x02020202u);   // bytes >= 2: not VERTEX / LEFT
+			}
+			other = __reduce_add_sync(0xffffffffu, other);
+			if((tid & 31u) == 0) atomicAdd(&sh.flag, other);
+			__syncthreads();
+			const uint32_t irregular = ns >= 1024u && sh.flag*8u > ns;
+			__syncthreads();
+			if(tid == 0) sh.flag = 0;
+			if(irregular) { if(tid == 0) B.regular[mi] = 0x80000000u; continue; }
+		}
 		if(tid == 0) { merged_init(sh.S); sh.mode = 0; sh.tried = 0; sh.windowed = 0; }
 		int mode;
 		for(;;) {
@@ -467,10 +487,9 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 	}
 }
 
-int launch_clers_cta(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, uint32_t runmin, cudaStream_t s) {
+int launch_clers_cta(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, bool defer, cudaStream_t s) {
 	// ring size: as much shared memory per mesh as leaves every mesh of the batch resident (up to 4 CTAs of 256 threads per SM);
 	// windows of 1024 symbols where the ring is large enough to keep two of them plus a strip of reach-back, else 512
-	(void)runmin;
 	uint32_t R = 8192;
 	if(nwork > (uint32_t)sms) R = 4096;
 	if(nwork > 2u*(uint32_t)sms) R = 2048;
@@ -480,11 +499,11 @@ int launch_clers_cta(const DevBatch &B, const uint32_t *order, uint32_t nwork, c
 	if(R >= 4096) {
 		e = cudaFuncSetAttribute(k_clers_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e != cudaSuccess) return (int)e;
-		k_clers_cta<4><<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R);
+		k_clers_cta<4><<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R, defer);
 	} else {
 		e = cudaFuncSetAttribute(k_clers_cta<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e != cudaSuccess) return (int)e;
-		k_clers_cta<2><<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R);
+		k_clers_cta<2><<<g, CT, smem, s>>>(B, order, nwork, scratch, ticket, R, defer);
 	}
 	e = cudaGetLastError();
 	return e == cudaSuccess ? 0 : (int)e;

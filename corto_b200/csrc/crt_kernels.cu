@@ -723,7 +723,7 @@ constexpr uint32_t LF_LOG = 2048;       // log ring words
 constexpr uint32_t LF_SPIN = 1u << 26;  // bound on every wait loop
 
 __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mesh_order, uint32_t nwork, ClersScratch scratch, uint32_t *ticket,
-                                                  uint32_t RB, uint32_t RA, bool vecmode) {
+                                                  uint32_t RB, uint32_t RA, bool vecmode, bool only_deferred) {
 	__shared__ uint32_t ctl[8];          // 0 head, 1 tail, 2 done, 3 abort, 4 mesh, 5 lead rc
 	__shared__ uint32_t chain[33];       // prev-chain of a VERTEX/LEFT window (lead_vector)
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -741,6 +741,11 @@ __global__ void __launch_bounds__(64) k_clers_lf(DevBatch B, const uint32_t *mes
 		const uint32_t w = ctl[4];
 		if(w >= nwork) break;
 		const uint32_t mi = mesh_order[w];
+		if(only_deferred) {                    // second pass behind k_clers_cta: only the meshes it left (uniform: one word per mesh)
+			if(!(B.regular[mi] >> 31)) continue;
+			__syncthreads();
+			if(threadIdx.x == 0) B.regular[mi] = 0;
+		}
 		const MeshDesc *M = B.mesh + mi;
 		const TunDesc td = B.tun[M->clers_tun];
 		ClersIO io;
@@ -2036,14 +2041,21 @@ int launch_tun_decode(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uin
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(nwork == 0) return 0;
 	// CORTO_CLERS: 1 one warp per mesh (clers_run), 2 leader / follower warps, scalar, 3 leader / follower + 32-wide window steps,
-	// default (4): one CTA per mesh, 256-wide window steps (k_clers_cta, crt_clers_cta.cu); CORTO_RUNMIN = shortest run it takes
-	static int mode = -1, runmin = 4;
+	// 4: one CTA per mesh, CTA-wide window steps (k_clers_cta, crt_clers_cta.cu) for every mesh; default: the same for meshes whose
+	// stream is regular, k_clers_lf for the others
+	static int mode = -1;
 	if(mode < 0) {
-		const char *e = getenv("CORTO_CLERS"), *r = getenv("CORTO_RUNMIN");
-		if(r && atoi(r) >= 2 && atoi(r) <= 32) runmin = atoi(r);
-		mode = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 4;
+		const char *e = getenv("CORTO_CLERS");
+		mode = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : ((e && e[0] == '4') ? 5 : 4);
 	}
-	if(mode == 4) return launch_clers_cta(B, order, nwork, scratch, ticket, sms, (uint32_t)runmin, s);
+	// default: k_clers_cta takes the meshes whose stream sample is regular and defers the others (B.regular bit 31) to k_clers_lf,
+	// launched right behind it with its own ticket (ticket[1]); CORTO_CLERS=4 keeps everything on k_clers_cta
+	const bool only_deferred = mode == 4 || mode == 5;
+	if(only_deferred) {
+		int rc = launch_clers_cta(B, order, nwork, scratch, ticket, sms, mode == 4, s);
+		if(rc || mode == 5) return rc;
+		ticket += 1;
+	}
 	const uint32_t g = nwork < scratch.slots ? nwork : scratch.slots;
 	if(mode == 1) {
 		uint32_t R = 4096, Q = 2048;
@@ -2060,7 +2072,7 @@ int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const
 		const size_t smem = (size_t)RB*9 + (size_t)LF_LOG*4 + (size_t)RA*16 + 2*(size_t)LF_STAGE*16;
 		cudaError_t e = cudaFuncSetAttribute(k_clers_lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: not cached
 		if(e != cudaSuccess) return (int)e;
-		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, RA, mode == 3);
+		k_clers_lf<<<g, 64, smem, s>>>(B, order, nwork, scratch, ticket, RB, RA, mode >= 3, only_deferred);
 	}
 	LAUNCH_CHECK(); return 0;
 }

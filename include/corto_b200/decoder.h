@@ -8,9 +8,13 @@
 //   decoder.decode();                         // blob H2D -> CUDA kernels -> outputs D2H, synchronous
 //
 // Same names, same argument meaning, same error behaviour: failures throw `const char *` like the reference
-// (src/decoder.cpp:44,51,274).  What is NOT here: the encoder side (quantize/encode members) and CPU decode virtuals —
-// attribute objects are plain descriptors; replacing an attribute with a user subclass (setAttribute(name, buf, attr*))
-// keeps the reference's ownership rule but the device decode always uses the stream's codec.
+// (src/decoder.cpp:44,51,274).  What is NOT here: the encoder side (quantize/encode members) and the CPU decode virtuals
+// (decode / deltaDecode / postDelta / dequantize, vertex_attribute.h:48-66): attribute objects are plain descriptors, the
+// decode runs on the device with the codec the stream names.  setAttribute(name, buf, attr*) keeps the reference's ownership
+// rule; an object whose codec() differs from the stream's (a user subclass with its own decode) cannot be honoured and is
+// refused with a thrown message instead of being silently ignored.
+// The same header is reachable under the reference's own include names (include/corto/decoder.h, corto.h, ...), so user
+// code compiles unchanged with -I<this repo>/include.
 #ifndef CORTO_B200_DECODER_H
 #define CORTO_B200_DECODER_H
 
@@ -28,6 +32,28 @@ typedef unsigned char uchar;
 namespace crt {
 
 struct Face { uint32_t a, b, c; Face() {} Face(uint32_t v0, uint32_t v1, uint32_t v2): a(v0), b(v1), c(v2) {} };
+
+// The small fixed-size vectors the attribute statics take and return (include/corto/point.h:29-185: Point2s / Point2i /
+// Point2f / Point3s / Point3i / Point3f); only what a decoder-side caller touches: construction, operator[], norm().
+template <typename S, int D> class PointN {
+	S v[D];
+public:
+	PointN() {}
+	PointN(S x, S y) { static_assert(D == 2, "two components"); v[0] = x; v[1] = y; }
+	PointN(S x, S y, S z) { static_assert(D == 3, "three components"); v[0] = x; v[1] = y; v[2] = z; }
+	explicit PointN(const S *x) { for(int k = 0; k < D; k++) v[k] = x[k]; }
+	S &operator[](int k) { return v[k]; }
+	const S &operator[](int k) const { return v[k]; }
+	bool operator==(const PointN &o) const { for(int k = 0; k < D; k++) if(v[k] != o.v[k]) return false; return true; }
+	bool operator!=(const PointN &o) const { return !(*this == o); }
+	S norm() const { S s = v[0]*v[0]; for(int k = 1; k < D; k++) s = s + v[k]*v[k]; return (S)sqrt((double)s); }   // point.h:59,111
+};
+typedef PointN<int16_t, 2> Point2s;
+typedef PointN<int32_t, 2> Point2i;
+typedef PointN<float, 2> Point2f;
+typedef PointN<int16_t, 3> Point3s;
+typedef PointN<int32_t, 3> Point3i;
+typedef PointN<float, 3> Point3f;
 
 struct Group {                                   // include/corto/index_attribute.h:40-46
 	uint32_t end;
@@ -74,6 +100,50 @@ public:
 	uint32_t prediction;
 	NormalAttr(int bits = 10) { N = 3; q = powf(2.0f, (float)(bits - 1)); prediction = DIFF; strategy |= VertexAttribute::CORRELATED; }
 	virtual int codec() { return NORMAL_CODEC; }
+
+	// Octahedral mapping, host side (normal_attribute.h:75-122) — the same arithmetic the device kernels emulate (crt_device.cuh:
+	// to_octa / to_sphere): fp32 throughout, one divisor for both components, truncating float -> int conversions.
+	static Point2i toOcta(Point3f n, int unit) {                       // normal_attribute.h:75-85
+		const float l1 = fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]);
+		float x = n[0]/l1, y = n[1]/l1;
+		if(n[2] < 0) {
+			const float fx = 1.0f - fabsf(y), fy = 1.0f - fabsf(x);
+			x = n[0] < 0 ? -fx : fx;
+			y = n[1] < 0 ? -fy : fy;
+		}
+		return Point2i((int)(x*unit), (int)(y*unit));
+	}
+	static Point2i toOcta(Point3i n, int unit) {                       // normal_attribute.h:87-102 (integer variant)
+		const int l1 = abs(n[0]) + abs(n[1]) + abs(n[2]);
+		if(l1 == 0) return Point2i(0, 0);
+		int x = n[0]*unit/l1, y = n[1]*unit/l1;
+		if(n[2] < 0) {
+			const int fx = (int)(unit - fabs(y)), fy = (int)(unit - fabs(x));
+			x = n[0] < 0 ? -fx : fx;
+			y = n[1] < 0 ? -fy : fy;
+		}
+		return Point2i(x, y);
+	}
+	static Point3f toSphere(Point2i v, int unit) {                     // normal_attribute.h:104-112
+		float n[3];
+		octa_to_vector(v[0], v[1], unit, n);
+		return Point3f(n[0], n[1], n[2]);
+	}
+	static Point3s toSphere(Point2s v, int unit) {                     // normal_attribute.h:114-122
+		float n[3];
+		octa_to_vector(v[0], v[1], unit, n);
+		return Point3s((int16_t)(n[0]*32767), (int16_t)(n[1]*32767), (int16_t)(n[2]*32767));
+	}
+private:
+	static void octa_to_vector(int vx, int vy, int unit, float n[3]) {
+		n[0] = (float)vx; n[1] = (float)vy; n[2] = (float)(unit - abs(vx) - abs(vy));
+		if(n[2] < 0) {                                                 // lower hemisphere: fold back; sgn(0) counts as -1
+			n[0] = (float)((vx > 0 ? 1 : -1)*(unit - abs(vy)));
+			n[1] = (float)((vy > 0 ? 1 : -1)*(unit - abs(vx)));
+		}
+		const float len = (float)sqrt((double)(n[0]*n[0] + n[1]*n[1] + n[2]*n[2]));
+		n[0] /= len; n[1] /= len; n[2] /= len;
+	}
 };
 
 class ColorAttr: public GenericAttr<uchar> {     // color_attribute.h:26-42
@@ -137,6 +207,14 @@ public:
 	bool setAttribute(const char *name, char *buffer, VertexAttribute *attr) {            // src/decoder.cpp:104-114 (takes ownership)
 		if(data.find(name) == data.end()) return false;
 		VertexAttribute *found = data[name];
+		if(attr->codec() != found->codec()) {                                             // a user codec: the device cannot run its virtuals
+			delete attr;                                                                  // (ownership was transferred)
+#ifndef NO_EXCEPTIONS
+			throw "corto_b200: custom attribute codecs are not supported (the decode runs on the device with the stream's codec)";
+#else
+			return false;
+#endif
+		}
 		attr->q = found->q; attr->strategy = found->strategy; attr->N = found->N; attr->buffer = buffer;
 		delete data[name];
 		data[name] = attr;

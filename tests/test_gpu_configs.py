@@ -57,7 +57,7 @@ print("ok", n, int(bd.total_verts))
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("clers", ["default", "3"])
+@pytest.mark.parametrize("clers", ["default", "3", "4"])
 def test_c4_batch_640(clers, tmp_path):
     if not refshim.available():
         pytest.skip("needs the reference shim to encode")
@@ -108,6 +108,34 @@ def test_tarta_batch_of_4():
         for k, w in want.items():
             if isinstance(w, np.ndarray):
                 assert np.array_equal(got[k].view(np.uint8).reshape(-1), w.view(np.uint8).reshape(-1)), (i, k)
+
+
+@pytest.mark.timeout(600)
+def test_regular_and_irregular_meshes_in_one_batch():
+    """The default CLERS launch splits a batch by a sample of each stream: regular meshes stay on k_clers_cta, irregular ones (the
+    real scan) go to k_clers_lf behind it.  Both kinds in one batch, twice (the deferral flags live in the zeroed control region)."""
+    import torch
+    from oracle import workloads
+    if not os.path.exists(refshim.TARTA) or not refshim.available():
+        pytest.skip("needs tarta.crt and the reference encoder")
+    tarta = refshim.aligned_blob(open(refshim.TARTA, "rb").read())
+    grid = workloads._c2(7)
+    blobs = [tarta, grid, tarta, workloads._c2(8)]
+    want = [pyoracle.decode(b) for b in (tarta, grid, tarta, blobs[3])]
+    bd = corto_b200.BatchDecoder(blobs)
+    bd.allocate(fill=0xA5)
+    bd.upload()
+    for _ in range(2):
+        bd.decode()
+        torch.cuda.synchronize()
+        rc, st = bd.status()
+        assert rc == 0, st
+        for i, w in enumerate(want):
+            got = bd.mesh_outputs(i)
+            for k, x in w.items():
+                if isinstance(x, np.ndarray):
+                    assert np.array_equal(got[k].view(np.uint8).reshape(-1), x.view(np.uint8).reshape(-1)), (i, k)
+        bd.rewalk()
 
 
 @pytest.mark.parametrize("name,formats", [

@@ -159,10 +159,11 @@ def test_tarta():
             _same("tarta/" + k, got[k], w)
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "runmin2", "runmin9", "split0", "split1", "deltacta", "deltaseq", "deltawarp", "tunseq", "unpackchain", "overlap1", "adjagg1"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "split0", "split1", "deltacta", "deltaseq", "deltawarp", "tunseq", "unpackchain", "overlap1", "adjagg1"])
 def test_alternative_clers_machines(mode, tmp_path):
-    """CORTO_CLERS=1 (single-warp lazy-front machine) and =2 (leader/follower without window steps) stay bit-exact: they are the
-    A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
+    """CORTO_CLERS=1 (single-warp lazy-front machine), =2 / =3 (leader/follower without / with window steps for every mesh) and =4
+    (the CTA machine for every mesh, irregular ones included; the default hands those to the leader/follower kernel) stay
+    bit-exact: they are the A/B baselines DESIGN.md section 5 quotes, selected once per process by the environment."""
     import os
     import subprocess
     import sys
@@ -187,8 +188,6 @@ print("ok")
         extra = {"CORTO_DELTA_SPLIT": mode[-1]}
     elif mode == "deltacta":                      # the block-wide delta kernel (sub-blocks + pointer doubling through shared memory)
         extra = {"CORTO_DELTA": "cta"}
-    elif mode.startswith("runmin"):               # k_clers_cta with another run threshold for its CTA-wide windows
-        extra = {"CORTO_RUNMIN": mode[6:]}
     elif mode == "deltawarp":                     # the warp-per-chain delta kernel for every mesh (default: segmented-scan rounds for regular meshes)
         extra = {"CORTO_DELTA": "warp"}
     elif mode == "tunseq":                        # the one-thread Tunstall dictionary build (default: warp-cooperative)
