@@ -57,6 +57,7 @@ struct crt_batch {
 	std::vector<Tile> t_tun, t_bits, t_dequant, t_faces, t_verts, t_vscan, t_cfused;
 	std::vector<uint2> w_delta;
 	std::vector<uint32_t> c_bits;      // per unpack chain (mesh, attribute): index of its first tile in t_bits, + one sentinel
+	std::vector<uint32_t> c_cfused;    // the same for the point-cloud chains (t_cfused)
 	std::vector<uint32_t> clers_order;
 	bool any_border = false;
 
@@ -71,7 +72,7 @@ struct crt_batch {
 	uint8_t *d_zero = nullptr;         size_t zero_bytes = 0;       // region cleared at every decode: tickets, states, status, csr counters
 	// offsets inside d_tables
 	size_t o_mesh = 0, o_tun = 0, o_groups = 0, o_t_tun = 0, o_t_bits = 0, o_t_dequant = 0, o_t_faces = 0, o_t_verts = 0,
-	       o_t_vscan = 0, o_w_delta = 0, o_order = 0, o_t_cfused = 0, o_c_bits = 0;
+	       o_t_vscan = 0, o_w_delta = 0, o_order = 0, o_t_cfused = 0, o_c_bits = 0, o_c_cfused = 0;
 	// offsets inside d_zero
 	size_t z_ticket = 0, z_status = 0, z_vcount = 0, z_regular = 0, z_states = 0, z_csr = 0, z_tunbits = 0;
 	bool delta_split = false;          // irregular meshes: one warp per component (small batches)
@@ -523,6 +524,10 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->o_w_delta = put(img, b->w_delta);
 	b->o_order = put(img, b->clers_order);
 	b->o_t_cfused = put(img, b->t_cfused);
+	b->c_cfused.clear();
+	for(size_t t = 0; t < b->t_cfused.size(); t++) if(b->t_cfused[t].first) b->c_cfused.push_back((uint32_t)t);
+	b->c_cfused.push_back((uint32_t)b->t_cfused.size());
+	b->o_c_cfused = put(img, b->c_cfused);
 	if(!b->d_tables || b->tables_bytes < img.size()) {
 		if(b->d_tables) { cudaFree(b->d_tables); b->d_tables = nullptr; }
 		CU(cudaMalloc(&b->d_tables, img.size() + 256));
@@ -647,7 +652,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	}
 	RUN(launch_mesh_unpack(B, t_bits, (uint32_t)b->t_bits.size(), (const uint32_t *)(b->d_tables + b->o_c_bits), (uint32_t)b->c_bits.size() - 1u, st_bits, tickets + 1, b->sms, s2), !b->t_bits.empty());
 	if((rc = mark(b, "bit_unpack", k, s))) return rc;
-	RUN(launch_cloud_fused(B, (const Tile *)(b->d_tables + b->o_t_cfused), (uint32_t)b->t_cfused.size(), st_cfused, tickets + 6, b->sms, s2), !b->t_cfused.empty());
+	RUN(launch_cloud_fused(B, (const Tile *)(b->d_tables + b->o_t_cfused), (uint32_t)b->t_cfused.size(), (const uint32_t *)(b->d_tables + b->o_c_cfused), (uint32_t)b->c_cfused.size() - 1u, st_cfused, tickets + 6, b->sms, s2), !b->t_cfused.empty());
 	if((rc = mark(b, "cloud_fused", k, s))) return rc;
 	if(ovl) {
 		CU(cudaEventRecord(b->ev_join[0], s2));

@@ -391,21 +391,28 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 		const uint32_t nseg = (io.nclers + CTA_SEG - 1u)/CTA_SEG;
 		uint32_t issued = 0, ready = 0, hint = WS;
 		// Irregular meshes (real scans: runs of ~6 symbols between RIGHT / DELAY / BOUNDARY) gain nothing from CTA-wide windows and
-		// pay for the barriers: a sample of the stream decides, and such a mesh is left to the leader / follower kernel that
+		// pay for the barriers: a sample of the stream (how many RIGHT / DELAY symbols — BOUNDARY is common on regular meshes
+		// too: every strip of a grid ends in two) decides, and such a mesh is left to the leader / follower kernel that
 		// launch_clers_cta starts right after this one (B.regular[mi] bit 31 = "deferred").
 		if(defer) {
-			const uint32_t ns = min(io.nclers, 16384u) & ~15u;
+			// 16 chunks of 1 KB spread over the stream (streams shorter than 32 K symbols are not worth a second kernel)
+			const uint32_t ns = io.nclers >= 32768u ? 16384u : 0u;
 			uint32_t other = 0;
-			for(uint32_t i = tid*16u; i < ns; i += CT*16u) {
-				const uint4 q = *(const uint4 *)(io.clers + i);
+			for(uint32_t p = 0; p < 4u && ns; p++) {
+				const uint32_t chunk = p*4u + (tid >> 6);
+				const uint32_t at = (((io.nclers >> 4)*chunk) & ~15u) + (tid & 63u)*16u;      // < nclers - 1024 + 1024
+				const uint4 q = *(const uint4 *)(io.clers + at);
 				const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-				for(int k = 0; k < 4; k++) other += (uint32_t)__popc((ws[k] | (ws[k] >> 1)) & 0x02020202u);   // bytes >= 2: not VERTEX / LEFT
+				for(int k = 0; k < 4; k++) {
+#pragma unroll
+					for(int j = 0; j < 4; j++) { const uint32_t c = (ws[k] >> (8*j)) & 0xffu; other += (c == (uint32_t)C_RIGHT || c == (uint32_t)C_DELAY) ? 1u : 0u; }
+				}
 			}
 			other = __reduce_add_sync(0xffffffffu, other);
 			if((tid & 31u) == 0) atomicAdd(&sh.flag, other);
 			__syncthreads();
-			const uint32_t irregular = ns >= 1024u && sh.flag*8u > ns;
+			const uint32_t irregular = ns && sh.flag*16u > ns;     // > 6 % RIGHT / DELAY (a real scan: ~14 %; grids ~0, a grid with a punched hole up to 3 %)
 			__syncthreads();
 			if(tid == 0) sh.flag = 0;
 			if(irregular) { if(tid == 0) B.regular[mi] = 0x80000000u; continue; }

@@ -252,7 +252,7 @@ constexpr uint32_t TUN_STAGE = 16384;   // output bytes of one tile assembled in
 __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket) {
 	__shared__ __align__(16) uint32_t s_entry[256];
 	__shared__ __align__(16) uint8_t s_text[TUN_TABLE_BYTES];
-	__shared__ __align__(16) uint8_t s_stage[TUN_STAGE];
+	__shared__ __align__(16) uint8_t s_stage[TUN_STAGE + 32];
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ uint32_t s_warp[9];
 	__shared__ uint32_t s_tile;
@@ -304,19 +304,39 @@ __global__ void __launch_bounds__(256) k_tun_decode(DevBatch B, const Tile *tile
 		const uint64_t obase = s_base;
 		uint32_t ssum = 0;
 		if(total <= TUN_STAGE && obase + total <= td.size && !(tl.tile*TUN_TILE + TUN_TILE >= td.csize)) {
-			// common case: the tile's words are assembled in shared memory, then written with coalesced stores
-			uint32_t o = off;
+			// common case: the tile's words are assembled in shared memory — at the byte phase (obase & 15) of their place in the
+			// output, so that 16-byte chunks of the stage ARE 16-byte chunks of the output — then written with 128-bit stores
+			// (the symbol arena aligns every block to 16 bytes, crt_api.cu: add_block)
+			const uint32_t ph = (uint32_t)obase & 15u;
+			uint32_t o = ph + off;
 #pragma unroll
 			for(int j = 0; j < 8; j++) {
 				const uint32_t i = i0 + j;
 				if(i >= td.csize) break;
 				const uint32_t e = s_entry[by[j]];
-				const uint32_t st = e & 0xffffu, len = e >> 16;
-				for(uint32_t k = 0; k < len; k++) { const uint8_t v = s_text[(st + k) & (TUN_TABLE_BYTES - 1)]; s_stage[o + k] = v; ssum += v; }
-				o += len;
+				uint32_t st = e & 0xffffu, len = e >> 16;
+				while(len) {                                   // eight text bytes per step: two aligned words, funnel-shifted
+					const uint32_t a = st & ~3u, sh = (st & 3u)*8u;
+					const uint32_t w0 = *(const uint32_t *)(s_text + (a & (TUN_TABLE_BYTES - 1))), w1 = *(const uint32_t *)(s_text + ((a + 4u) & (TUN_TABLE_BYTES - 1))),
+					               w2 = *(const uint32_t *)(s_text + ((a + 8u) & (TUN_TABLE_BYTES - 1)));
+					uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+					const uint32_t n = len < 8u ? len : 8u;
+					if(n < 4u) { lo &= (1u << (8u*n)) - 1u; hi = 0; } else if(n < 8u) hi &= (1u << (8u*(n - 4u))) - 1u;
+					ssum = __dp4a(lo, 0x01010101u, ssum); ssum = __dp4a(hi, 0x01010101u, ssum);
+#pragma unroll
+					for(int k = 0; k < 4; k++) if((uint32_t)k < n) s_stage[o + k] = (uint8_t)(lo >> (8*k));
+#pragma unroll
+					for(int k = 0; k < 4; k++) if((uint32_t)(k + 4) < n) s_stage[o + 4 + k] = (uint8_t)(hi >> (8*k));
+					o += n; st += n; len -= n;
+				}
 			}
 			__syncthreads();
-			for(uint32_t i = tid; i < total; i += 256) out[obase + i] = s_stage[i];
+			const uint32_t head = ph ? 16u - ph : 0u;          // bytes up to the first 16-byte boundary of the output
+			const uint32_t nvec = total > head ? (total - head) >> 4 : 0u, tail0 = head + (nvec << 4);
+			uint8_t *dst = out + obase;
+			for(uint32_t i = tid; i < nvec; i += 256) *(uint4 *)(dst + head + (i << 4)) = *(const uint4 *)(s_stage + ph + head + (i << 4));
+			if((uint32_t)tid < head && (uint32_t)tid < total) dst[tid] = s_stage[ph + tid];
+			if(total > head) { const uint32_t t2 = tail0 + (uint32_t)tid; if(tid < 16 && t2 < total) dst[t2] = s_stage[ph + t2]; }
 		} else {
 			// long words, the last tile of a block (its last byte is clipped, tunstall.cpp:446-451) or a corrupt stream: direct stores
 			uint64_t o = obase + off;
@@ -1853,7 +1873,10 @@ __device__ __forceinline__ void cloud_tile(const DevBatch &B, const MeshDesc *M,
 		tsum[k] = r[k][3];
 	}
 	cta_scan_multi<NC>(tsum, vexcl, vtot, s_w);
-	if(tid < NC) s_base[tid] = lookback_strided(states, tile_id, 8, 4u + (uint32_t)tid, first, vtot[tid]);
+	if(tid < NC) {
+		if(s_carry) { s_base[tid] = s_carry[4 + tid]; s_carry[4 + tid] += vtot[tid]; }      // one CTA walks the chain: running sums
+		else s_base[tid] = lookback_strided(states, tile_id, 8, 4u + (uint32_t)tid, first, vtot[tid]);
+	}
 	__syncthreads();
 #pragma unroll
 	for(int k = 0; k < NC; k++) {
@@ -1963,6 +1986,34 @@ __global__ void __launch_bounds__(256, MINB) k_unpack_chain(DevBatch B, const Ti
 		case 2: cloud_tile<2, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
 		case 3: cloud_tile<3, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
 		default: cloud_tile<4, true>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		}
+		__syncthreads();                             // s_w / s_base / s_out are reused by the next tile
+	}
+}
+
+// Point clouds, one CTA per chain (all tiles of one attribute of one cloud, in order): both carries — the bit offset of every
+// log stream and the running sum of every component — live in shared memory, so there is no look-back at all.  Used when the
+// batch has enough chains to fill the GPU (launch_cloud_fused); the ticketed look-back kernel stays for a few large clouds.
+__global__ void __launch_bounds__(256, 5) k_cloud_chain(DevBatch B, const Tile *tiles, const uint32_t *heads, uint32_t nchains) {
+	__shared__ uint32_t s_w[4][9];
+	__shared__ uint64_t s_base[4], s_carry[8];
+	__shared__ __align__(16) uint8_t s_out[1024*16];
+	const uint32_t c = blockIdx.x;
+	if(c >= nchains) return;
+	if(threadIdx.x < 8) s_carry[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t t0 = heads[c], t1 = heads[c + 1];
+	Tile tl = tiles[t0];
+	const MeshDesc *M = B.mesh + tl.a;
+	const AttrDesc *A = &M->attr[tl.b];
+	const int nc = A->ncomp;
+	for(uint32_t t = t0; t < t1; t++) {
+		tl.tile = t - t0; tl.first = t == t0 ? 1u : 0u;
+		switch(nc) {
+		case 1: cloud_tile<1, false>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		case 2: cloud_tile<2, false>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		case 3: cloud_tile<3, false>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
+		default: cloud_tile<4, false>(B, M, A, tl, t, nullptr, s_w, s_base, s_out, s_carry); break;
 		}
 		__syncthreads();                             // s_w / s_base / s_out are reused by the next tile
 	}
@@ -2109,9 +2160,13 @@ int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles
 	k_normal_estimate<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
+int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, const uint32_t *heads, uint32_t nchains, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_unpack_fused<false><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
+	// one CTA per chain when there are enough chains to fill the GPU (CORTO_UNPACK=chain / lookback forces either, like the meshes)
+	static int mode = -1;
+	if(mode < 0) { const char *e = getenv("CORTO_UNPACK"); mode = (e && e[0] == 'c') ? 1 : ((e && e[0] == 'l') ? 2 : 0); }
+	if(mode == 1 || (mode == 0 && nchains >= 2u*(uint32_t)sms)) k_cloud_chain<<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+	else k_unpack_fused<false><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, const uint32_t *heads, uint32_t nchains, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {

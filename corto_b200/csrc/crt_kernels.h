@@ -38,6 +38,6 @@ int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cuda
 int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s);
 int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
 int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
-int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s);
+int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, const uint32_t *heads, uint32_t nchains, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s);
 
 }  // namespace crtb
