@@ -56,8 +56,20 @@ def parse():
     return p.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_clers_lf per c2 mesh (profiles/r1_k_clers_lf_ncu_raw.txt: 16 meshes)
-TRAFFIC_CLERS_C2_PER_MESH = int((4.281856e6 + 73.254656e6) / 16)
+def measured_traffic(kernel, workload, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture of the SAME launch
+    configuration (profiles/r2_traffic_c2.json: 256 x configs[1]); None for any other kernel / workload / batch — never a constant."""
+    if workload != "c2" or batch != 256:
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic_c2.json")))["kernels"]
+        for name, v in d.items():
+            if name.split("<")[0] == kernel.split("<")[0].split(" ")[0]:
+                return int(v["dram_bytes_read"] + v["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
 
 DEFAULT_BATCH = dict(c1=1, c2=256, c3=512, c4=512, c5=1, tarta=64)
 
@@ -366,20 +378,19 @@ def main():
     roof = None
     if dom:
         ach = (in_bytes + out_bytes) / (stage_ms[dom] * 1e-3) / 1e9
-        kernel_of = {"clers": "k_clers_lf", "delta": "k_delta_mesh", "cloud_fused": "k_unpack_fused<CLOUD>", "tun_decode": "k_tun_decode",
-                     "bit_unpack": "k_unpack_chain / k_unpack_fused<MESH>", "normals": "k_adj_build + k_normal_estimate", "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/): measured per mesh on a 16-mesh
-        # batch of this workload, scaled to this batch; null where no capture exists for the kernel/workload pair
-        traffic = None
-        if dom == "clers" and args.workload == "c2":
-            traffic = TRAFFIC_CLERS_C2_PER_MESH * batch
+        kernel_of = {"clers": "k_clers_cta (+ k_clers_lf for irregular meshes)", "delta": "k_delta_mesh_seg", "cloud_fused": "k_cloud_chain / k_unpack_fused<CLOUD>",
+                     "tun_decode": "k_tun_decode", "bit_unpack": "k_unpack_chain / k_unpack_fused<MESH>", "normals": "k_adj_build + k_normal_estimate",
+                     "dequant": "k_dequant", "tun_tables": "k_tun_tables"}
+        traffic = measured_traffic(kernel_of.get(dom, dom), args.workload, batch)
         roof = {"bound": "hbm", "kernel": kernel_of.get(dom, dom), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
                 "algorithmic_bytes": {"blobs": in_bytes, "outputs": out_bytes},
                 "step_achieved": (in_bytes + out_bytes) * args.steps / (ms * 1e-3) / 1e9,
                 "read_only_frac": in_bytes / (stage_ms[dom] * 1e-3) / 1e9 / peak,
                 "stage_ms_from": "a re-run of the same steps right after the timed region with the library's stage timers (CUDA events) on",
-                "note": "mesh decode is bound by the serial CLERS automaton (instruction latency, not HBM); see DESIGN.md section 5"}
+                "traffic_source": "profiles/r2_traffic_c2.json (ncu --set full of this launch configuration)" if traffic else None,
+                "note": "no kernel of the mesh path is HBM-bound except the normal estimation (61 % of peak DRAM throughput); the others are bound by "
+                        "dependent-instruction latency at low occupancy (CLERS: one CTA per mesh) or by issue rate; see DESIGN.md sections 4-5"}
     launches = bd.launches * args.steps
     verts_per_gpu, faces_per_gpu = int(bd.total_verts), int(bd.total_faces)
 

@@ -1994,7 +1994,8 @@ __global__ void __launch_bounds__(256, MINB) k_unpack_chain(DevBatch B, const Ti
 // Point clouds, one CTA per chain (all tiles of one attribute of one cloud, in order): both carries — the bit offset of every
 // log stream and the running sum of every component — live in shared memory, so there is no look-back at all.  Used when the
 // batch has enough chains to fill the GPU (launch_cloud_fused); the ticketed look-back kernel stays for a few large clouds.
-__global__ void __launch_bounds__(256, 5) k_cloud_chain(DevBatch B, const Tile *tiles, const uint32_t *heads, uint32_t nchains) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_cloud_chain(DevBatch B, const Tile *tiles, const uint32_t *heads, uint32_t nchains) {
 	__shared__ uint32_t s_w[4][9];
 	__shared__ uint64_t s_base[4], s_carry[8];
 	__shared__ __align__(16) uint8_t s_out[1024*16];
@@ -2165,7 +2166,15 @@ int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, co
 	// one CTA per chain when there are enough chains to fill the GPU (CORTO_UNPACK=chain / lookback forces either, like the meshes)
 	static int mode = -1;
 	if(mode < 0) { const char *e = getenv("CORTO_UNPACK"); mode = (e && e[0] == 'c') ? 1 : ((e && e[0] == 'l') ? 2 : 0); }
-	if(mode == 1 || (mode == 0 && nchains >= 2u*(uint32_t)sms)) k_cloud_chain<<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+	if(mode == 1 || (mode == 0 && nchains >= 2u*(uint32_t)sms)) {
+		int o5 = 0, o6 = 0;                                    // the 6-CTA build when it saves a wave (see launch_mesh_unpack)
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, k_cloud_chain<5>, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o6, k_cloud_chain<6>, 256, 0);
+		bool six = false;
+		if(o5 > 0 && o6 > o5) six = (nchains + (uint32_t)(o6*sms) - 1u)/(uint32_t)(o6*sms) < (nchains + (uint32_t)(o5*sms) - 1u)/(uint32_t)(o5*sms);
+		if(six) k_cloud_chain<6><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+		else k_cloud_chain<5><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
+	}
 	else k_unpack_fused<false><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
 	LAUNCH_CHECK(); return 0;
 }
@@ -2175,11 +2184,21 @@ int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, co
 	static int mode = -1;
 	if(mode < 0) { const char *e = getenv("CORTO_UNPACK"); mode = (e && e[0] == 'c') ? 1 : ((e && e[0] == 'l') ? 2 : 0); }
 	const bool chain = mode == 1 || (mode == 0 && nchains >= 2u*(uint32_t)sms);
-	// 5 CTAs per SM at 48 registers; capping at 40 (a few spills) makes it 6, which pays exactly when it lets every chain be
-	// resident at once (configs[1]: 768 chains, 740 vs 888 slots: 1.02 -> 0.89 ms) and costs otherwise (configs[3]: 2.57 -> 2.78 ms)
-	static int occ = -1;                  // CORTO_UNPACK_OCC=5|6 forces either
+	// Two builds of the chain kernel: 48 registers (5 CTAs per SM by the occupancy calculator) and capped at 40 (a few spills, 6
+	// CTAs).  A chain is one CTA from start to end, so what matters is the number of WAVES the batch needs: the 6-CTA build is
+	// taken when it saves a wave (e.g. 768 chains on 148 SMs: 2 waves -> 1), never otherwise.  CORTO_UNPACK_OCC=5|6 forces either.
+	static int occ = -1;
 	if(occ < 0) { const char *e = getenv("CORTO_UNPACK_OCC"); occ = (e && (e[0] == '5' || e[0] == '6')) ? e[0] - '0' : 0; }
-	const bool six = occ == 6 || (occ == 0 && nchains > 5u*(uint32_t)sms && nchains <= 6u*(uint32_t)sms);
+	bool six = occ == 6;
+	if(occ == 0 && chain) {
+		int o5 = 0, o6 = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, k_unpack_chain<5>, 256, 0);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o6, k_unpack_chain<6>, 256, 0);
+		if(o5 > 0 && o6 > o5) {
+			const uint32_t w5 = (nchains + (uint32_t)(o5*sms) - 1u)/(uint32_t)(o5*sms), w6 = (nchains + (uint32_t)(o6*sms) - 1u)/(uint32_t)(o6*sms);
+			six = w6 < w5;
+		}
+	}
 	if(chain && six) k_unpack_chain<6><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
 	else if(chain) k_unpack_chain<5><<<nchains, 256, 0, s>>>(B, tiles, heads, nchains);
 	else k_unpack_fused<true><<<persistent_grid(ntiles, 6, sms), 256, 0, s>>>(B, tiles, ntiles, states, ticket);
