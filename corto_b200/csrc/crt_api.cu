@@ -370,13 +370,15 @@ static int build_tables(crt_batch *b, uint64_t &symbols_bytes, uint64_t &work_by
 			if(M.attr[M.position_attr].N != 3 || M.attr[M.position_attr].codec != CODEC_GENERIC)     // estimateNormals reads Point3i (normal_attribute.cpp:230)
 				return fail(CRT_E_LIMIT, "ESTIMATED/BORDER normals need a 3-component generic position attribute");
 			csr_off[i] = zero_csr_bytes;
-			zero_csr_bytes += align_up(((uint64_t)pm.nvert*3 + 2)*4, 16);      // cnt | bnd | cidx[+1] | novf
+			// cnt | ohead | novf, and for BORDER prediction bnd | cidx[+1] (crt_kernels.cu: adj_view)
+			const bool border_pred = pm.streams[M.normal_attr].prediction == N_BORDER;
+			zero_csr_bytes += align_up(((uint64_t)pm.nvert*(border_pred ? 4 : 2) + 3)*4, 16);
 			adj_off[i] = adj_bytes;
 			adj_bytes += align_up((uint64_t)pm.nface*16 + (uint64_t)pm.nvert*32 + (uint64_t)pm.nface*24, 16);   // face normals + 8 slots per vertex + overflow pairs
 			uint32_t nf = (pm.nface + SCAN_TILE - 1)/SCAN_TILE, nv = (pm.nvert + SCAN_TILE - 1)/SCAN_TILE, ns = (pm.nvert + 1 + SCAN_TILE - 1)/SCAN_TILE;
 			for(uint32_t t = 0; t < nf; t++) b->t_faces.push_back(Tile{(uint32_t)i, 0, t, 0});
 			for(uint32_t t = 0; t < nv; t++) b->t_verts.push_back(Tile{(uint32_t)i, 0, t, 0});
-			for(uint32_t t = 0; t < ns; t++) b->t_vscan.push_back(Tile{(uint32_t)i, 0, t, t == 0 ? 1u : 0u});
+			if(border_pred) for(uint32_t t = 0; t < ns; t++) b->t_vscan.push_back(Tile{(uint32_t)i, 0, t, t == 0 ? 1u : 0u});   // the boundary scan: BORDER meshes only (the others have no bnd / cidx)
 		}
 		// stash per-mesh work offsets (resolved to pointers once the arena address is known)
 		M.pred_ptr = pred_o; M.face_ptr = face_o;

@@ -1531,17 +1531,20 @@ __global__ void __launch_bounds__(32) k_delta_mesh(DevBatch B, const uint2 *work
 //     ORDER in fp32 (normal_attribute.cpp:44-55); fp32 addition is not associative, so instead of float atomics
 //     each vertex gathers its incident faces and adds them in ascending face index: bit-identical to the sequential
 //     loop for every input, no exactness guard needed.  Adjacency = 8 slots per vertex filled with one atomic per face
-//     corner (one pass over the faces), the rare vertex of higher valence spills (vertex, face) pairs to an overflow list.
-//     zeroed scratch per mesh (u32): cnt[nvert] | bnd[nvert] | cidx[nvert+1] | novf;   plain scratch: adj8[8*nvert] | ovf[3*nface] (uint2)
+//     corner (one pass over the faces); a vertex of higher valence chains its further faces through an overflow list
+//     (per-vertex linked lists: ohead[v] -> ovf[idx] = (face, next), so a high-valence vertex reads only its own entries).
+//     zeroed scratch per mesh (u32): cnt[nvert] | ohead[nvert] | novf | (BORDER only) bnd[nvert] | cidx[nvert+1];
+//     plain scratch: adj8[8*nvert] | ovf[3*nface] (uint2)
 // =========================================================================================================
-struct AdjView { uint32_t *cnt, *bnd, *cidx, *novf, *adj8; uint2 *ovf; float4 *fn; };
+struct AdjView { uint32_t *cnt, *bnd, *cidx, *novf, *ohead, *adj8; uint2 *ovf; float4 *fn; };
 __device__ __forceinline__ AdjView adj_view(const MeshDesc *M) {
 	AdjView c;
 	uint32_t *p = (uint32_t *)M->csr_ptr;
 	c.cnt = p; p += M->nvert;
-	c.bnd = p; p += M->nvert;
-	c.cidx = p; p += M->nvert + 1;
-	c.novf = p;
+	c.ohead = p; p += M->nvert;
+	c.novf = p; p += 1;
+	c.bnd = p; p += M->nvert;                        // (present for BORDER meshes only: crt_api.cu sizes the region by the prediction)
+	c.cidx = p;
 	c.fn = (float4 *)M->adj_ptr;
 	c.adj8 = (uint32_t *)(c.fn + M->nface);
 	c.ovf = (uint2 *)(c.adj8 + (size_t)M->nvert*8);
@@ -1595,7 +1598,10 @@ __global__ void __launch_bounds__(256) k_adj_build(DevBatch B, const Tile *tiles
 			} else if(valid) s = atomicAdd(C.cnt + v[k], 1u);
 			if(valid) {
 				if(s < 8) C.adj8[(size_t)v[k]*8 + s] = f;
-				else C.ovf[atomicAdd(C.novf, 1u)] = make_uint2(v[k], f);
+				else {                                     // valence > 8: push onto the vertex's own overflow chain (0 ends a chain)
+					const uint32_t idx = atomicAdd(C.novf, 1u);
+					C.ovf[idx] = make_uint2(f, atomicExch(C.ohead + v[k], idx + 1u));
+				}
 			}
 		}
 		if(border && valid) { atomicXor(C.bnd + v[0], v[1] ^ v[2]); atomicXor(C.bnd + v[1], v[2] ^ v[0]); atomicXor(C.bnd + v[2], v[0] ^ v[1]); }   // markBoundary :24-37
@@ -1628,6 +1634,44 @@ __global__ void __launch_bounds__(256) k_scan_u32(DevBatch B, const Tile *tiles,
 		const uint32_t e[4] = { base, base + s1, base + s2, base + s3 };
 #pragma unroll
 		for(int j = 0; j < 4; j++) { const uint32_t i = i0 + j; if(i <= n) C.cidx[i] = e[j]; }
+	}
+}
+
+// Valence > 8: the 8 slots + this vertex's overflow chain.  Up to 72 incident faces are copied to a local list and added by
+// repeated "smallest face id greater than the last one" (a face naming the vertex twice is added twice, like the reference's
+// corner loop); a fan pole beyond that walks the mesh's faces in order instead — O(nface) for that one vertex, but never
+// quadratic in the valence.
+__device__ __noinline__ void high_valence_normal(const MeshDesc *M, const AdjView &C, uint32_t i, uint32_t deg, float &ex, float &ey, float &ez) {
+	auto add_face = [&](uint32_t f) { const float4 n = C.fn[f]; ex = f_add(ex, n.x); ey = f_add(ey, n.y); ez = f_add(ez, n.z); };
+	constexpr uint32_t LOCAL = 72;
+	if(deg <= LOCAL) {
+		uint32_t fl[LOCAL];
+		uint32_t n = 0;
+		for(uint32_t s = 0; s < 8; s++) fl[n++] = C.adj8[(size_t)i*8 + s];
+		const uint32_t novf = *C.novf;
+		for(uint32_t at = C.ohead[i], guard = 0; at && at <= novf && n < deg && guard < LOCAL; guard++) { const uint2 e = C.ovf[at - 1u]; fl[n++] = e.x; at = e.y; }
+		int64_t last = -1;
+		uint32_t done = 0;
+		while(done < n) {
+			uint32_t fmin = 0xffffffffu, mult = 0;
+			for(uint32_t s = 0; s < n; s++) {
+				const uint32_t f = fl[s];
+				if((int64_t)f > last) { if(f < fmin) { fmin = f; mult = 1; } else if(f == fmin) mult++; }
+			}
+			if(mult == 0) break;
+			for(uint32_t m = 0; m < mult; m++) add_face(fmin);
+			done += mult;
+			last = (int64_t)fmin;
+		}
+	} else {
+		for(uint32_t f = 0; f < M->nface; f++) {
+			uint32_t a, b, c;
+			load_face(M, f, a, b, c);
+			if(a >= M->nvert || b >= M->nvert || c >= M->nvert) continue;      // (k_adj_build skipped it too)
+			if(a == i) add_face(f);
+			if(b == i) add_face(f);
+			if(c == i) add_face(f);
+		}
 	}
 }
 
@@ -1671,27 +1715,7 @@ __global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile 
 			if(deg > 6) add_face(f6);
 			if(deg > 7) add_face(f7);
 		} else {
-			// high valence (fan poles): repeated "smallest face id greater than the last one" over the 8 slots + this vertex's
-			// entries of the overflow list; a face naming the vertex twice is added twice, like the reference's corner loop
-			const uint32_t novf = *C.novf;
-			uint32_t done = 0;
-			int64_t last = -1;
-			while(done < deg) {
-				uint32_t fmin = 0xffffffffu, mult = 0;
-				for(uint32_t s = 0; s < 8; s++) {
-					const uint32_t f = C.adj8[(size_t)i*8 + s];
-					if((int64_t)f > last) { if(f < fmin) { fmin = f; mult = 1; } else if(f == fmin) mult++; }
-				}
-				for(uint32_t s = 0; s < novf; s++) {
-					const uint2 e = C.ovf[s];
-					if(e.x != i) continue;
-					if((int64_t)e.y > last) { if(e.y < fmin) { fmin = e.y; mult = 1; } else if(e.y == fmin) mult++; }
-				}
-				if(mult == 0) break;
-				for(uint32_t m = 0; m < mult; m++) add_face(fmin);
-				done += mult;
-				last = (int64_t)fmin;
-			}
+			high_valence_normal(M, C, i, deg, ex, ey, ez);            // out of line: keeps its local list out of the usual case's registers
 		}
 		if(!border || C.bnd[i] != 0u) {                               // computeNormals :288-293 / :315-319
 			int32_t qx, qy;

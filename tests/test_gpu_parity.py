@@ -57,6 +57,31 @@ def test_medium(name, builder):
     _check_blob(builder(), name)
 
 
+@pytest.mark.parametrize("n_lat,n_lon", [(10, 12), (8, 60), (6, 300), (4, 3000)])
+@pytest.mark.parametrize("pred", [1, 2])
+def test_high_valence_normals(n_lat, n_lon, pred):
+    """ESTIMATED / BORDER normals on UV spheres whose poles have valence n_lon: 12 and 60 go through the per-vertex overflow chains
+    (valence > 8 slots), 300 and 3000 through the in-order face scan of a fan pole — all bit-exact, and fast (the first version of
+    this path rescanned the whole overflow list per incident face: quadratic)."""
+    import time
+    if not refshim.available():
+        pytest.skip("needs the reference shim to encode")
+    from oracle import meshgen as mg
+    blob = refshim.encode(mg.sphere(n_lat, n_lon, 3), pos_bits=14, normal_bits=10, normal_pred=pred, with_uv=False, with_colors=False)[0]
+    want = refshim.decode(blob)
+    corto_b200.Decoder(blob).decode()                          # warm-up (context, allocations)
+    t0 = time.perf_counter()
+    got = corto_b200.Decoder(blob).decode()
+    dt = time.perf_counter() - t0
+    for k, w in want.items():
+        if isinstance(w, np.ndarray):
+            _same("sphere %dx%d pred %d/%s" % (n_lat, n_lon, pred, k), got[k], w)
+    assert dt < 0.5, dt
+    want16 = refshim.decode(blob, normals16=True)
+    got16 = corto_b200.Decoder(blob).decode(normals16=True)
+    _same("sphere int16 normals", got16["normal"], want16["normal"])
+
+
 def test_batch_from_device_arena():
     """crt_batch_create_device: the blobs exist in DEVICE memory only (one arena, as they arrive from the ingest rank over NVLink),
     the directory comes from their walk tapes; decode, re-walk + decode again — every array equals the oracle's."""
