@@ -55,7 +55,8 @@ struct crt_batch {
 	std::vector<TunDesc> h_tun;
 	std::vector<uint32_t> h_groups;
 	std::vector<Tile> t_tun, t_bits, t_dequant, t_faces, t_verts, t_vscan, t_cfused;
-	std::vector<uint2> w_delta;
+	std::vector<uint2> w_delta;        // delta work items; the first n_delta_crit are the positions an ESTIMATED / BORDER normal waits for
+	size_t n_delta_crit = 0;
 	std::vector<uint32_t> c_bits;      // per unpack chain (mesh, attribute): index of its first tile in t_bits, + one sentinel
 	std::vector<uint32_t> c_cfused;    // the same for the point-cloud chains (t_cfused)
 	std::vector<uint32_t> clers_order;
@@ -89,7 +90,7 @@ struct crt_batch {
 	std::vector<int> h_status;
 	// optional intra-batch overlap (CORTO_OVERLAP=1): the attribute unpack runs beside the CLERS automaton on a side stream
 	cudaStream_t side = nullptr;
-	cudaEvent_t ev_fork[1] = {nullptr}, ev_join[1] = {nullptr};
+	cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
 	int overlap = -1;                  // -1: read CORTO_OVERLAP on first use
 };
 
@@ -163,7 +164,7 @@ static void batch_free_device(crt_batch *b) {
 	b->d_tables = b->d_scratch = b->d_zero = nullptr;
 	for(auto &s: b->stages) cudaEventDestroy(s.ev);
 	b->stages.clear();
-	for(int k = 0; k < 1; k++) {
+	for(int k = 0; k < 2; k++) {
 		if(b->ev_fork[k]) cudaEventDestroy(b->ev_fork[k]);
 		if(b->ev_join[k]) cudaEventDestroy(b->ev_join[k]);
 		b->ev_fork[k] = b->ev_join[k] = nullptr;
@@ -523,6 +524,13 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 			for(unsigned c = 0; c < (w.y >> 16); c++) split.push_back(make_uint2(w.x, (w.y & 0xffu) | (c << 8)));
 		b->w_delta.swap(split);
 	}
+	// positions that a normal estimation waits for go first: CORTO_OVERLAP=2 runs the rest beside the estimation (crt_batch_decode)
+	{
+		auto crit = [&](const uint2 &w) { const MeshDesc &M = b->h_mesh[w.x]; return M.normal_attr >= 0 && (int)(w.y & 0xffu) == M.position_attr; };
+		std::stable_partition(b->w_delta.begin(), b->w_delta.end(), crit);
+		b->n_delta_crit = 0;
+		for(const uint2 &w: b->w_delta) if(crit(w)) b->n_delta_crit++;
+	}
 	b->o_w_delta = put(img, b->w_delta);
 	b->o_order = put(img, b->clers_order);
 	b->o_t_cfused = put(img, b->t_cfused);
@@ -628,17 +636,21 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
 	st += b->t_tun.size();
 	if((rc = mark(b, "tun_decode", k, s))) return rc;
-	// Stage order inside one batch.  Default: every stage on the caller's stream.  CORTO_OVERLAP=1 (attribute unpack beside the
-	// CLERS automaton on a side stream) is an experiment switch: the automaton leaves most SMs idle, but on B200 the company
-	// costs it more than it saves (measured on configs[1]: 13.1 ms overlapped vs 11.7 ms serial — the automaton's two warps per
-	// mesh lose issue slots and L1 to the wide kernel), so it is off unless asked for.  Stage timers (profiling) always run serial.
-	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 1 : 0; }
+	// Stage order inside one batch (CORTO_OVERLAP, two bits; stage timers — profiling — always run serial):
+	//   bit 0  the attribute unpack beside the CLERS automaton on a side stream.  The automaton leaves most issue slots idle, but the
+	//          company costs it about what it saves on configs[1] (7.76 vs 7.77 ms; round 1, two warps per mesh: 13.1 vs 11.7 ms);
+	//          it pays on configs[3], where CLERS is long (27.0 -> 24.0 ms with both bits).  Off by default.
+	//   bit 1  the delta inverse of everything a normal estimation does NOT wait for (uv, colours, ...) on the side stream beside
+	//          the adjacency build + estimation, which are HBM-bound and leave issue slots: configs[1] 7.76 -> 7.38 ms.  ON by default.
+	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 3 : 2; }
 	const bool ovl = (b->overlap & 1) && !b->profiling && !b->clers_order.empty() && !b->t_bits.empty();
+	// bit 1: the delta inverse of everything a normal estimation does NOT wait for (uv, colours, ...) runs beside the estimation
+	const bool ovl2 = (b->overlap & 2) && !b->profiling && !b->t_faces.empty() && b->n_delta_crit > 0 && b->n_delta_crit < b->w_delta.size();
 	cudaStream_t s2 = s;
-	if(ovl) {
+	if(ovl || ovl2) {
 		if(!b->side) {
 			CU(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
-			for(int k2 = 0; k2 < 1; k2++) {
+			for(int k2 = 0; k2 < 2; k2++) {
 				CU(cudaEventCreateWithFlags(&b->ev_fork[k2], cudaEventDisableTiming));
 				CU(cudaEventCreateWithFlags(&b->ev_join[k2], cudaEventDisableTiming));
 			}
@@ -663,6 +675,13 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 		RUN(launch_clers(B, (const uint32_t *)(b->d_tables + b->o_order), (uint32_t)b->clers_order.size(), b->clers, tickets + 2, b->sms, s), !b->clers_order.empty());
 	}
 	if((rc = mark(b, "clers", k, s))) return rc;
+	if(ovl2) {
+		const uint2 *wd = (const uint2 *)(b->d_tables + b->o_w_delta);
+		CU(cudaEventRecord(b->ev_fork[1], s));
+		CU(cudaStreamWaitEvent(b->side, b->ev_fork[1], 0));
+		RUN(launch_delta_mesh(B, wd, (uint32_t)b->n_delta_crit, b->delta_split, s), true);
+		RUN(launch_delta_mesh(B, wd + b->n_delta_crit, (uint32_t)(b->w_delta.size() - b->n_delta_crit), b->delta_split, b->side), true);
+	} else
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), b->delta_split, s), !b->w_delta.empty());
 	if((rc = mark(b, "delta", k, s))) return rc;
 	if(!b->t_faces.empty()) {                      // (the adjacency build reads the delta-decoded positions: it cannot move in front of the delta inverse)
@@ -670,6 +689,10 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
 		st += b->t_vscan.size();
 		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
+	}
+	if(ovl2) {
+		CU(cudaEventRecord(b->ev_join[1], b->side));
+		CU(cudaStreamWaitEvent(s, b->ev_join[1], 0));
 	}
 	if((rc = mark(b, "normals", k, s))) return rc;
 	RUN(launch_dequant(B, t_dequant, (uint32_t)b->t_dequant.size(), s), !b->t_dequant.empty());

@@ -128,6 +128,11 @@ __device__ int cta_window(const ClersIO &io, CtaRings &rg, CtaShared &sh, const 
 #pragma unroll
 		for(int h = 0; h < NH; h++) {
 			const uint32_t s = tid + (uint32_t)h*CT;
+			if((uint32_t)h*CT >= lim) {                        // nothing of the stream in this quarter (uniform): an immediate stop
+				bV[h] = bL[h] = 0;
+				if(lane == 0) sh.pk[it][w + (uint32_t)h*CTW] = 0u;
+				continue;
+			}
 			const uint32_t c = s < lim ? rg.sym(cler + s) : 0xffu;
 			bV[h] = __ballot_sync(FULL, c == C_VERTEX); bL[h] = __ballot_sync(FULL, c == C_LEFT);
 			const uint32_t stop = ~(bV[h] | bL[h]);
@@ -464,7 +469,8 @@ __global__ void __launch_bounds__(CT) k_clers_cta(DevBatch B, const uint32_t *me
 					// instructions per step
 					const uint32_t before = cler;
 					int r;
-					if(NHK >= 4 && hint > 2u*CT) r = cta_window<4>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
+					if(NHK >= 4 && hint > 3u*CT) r = cta_window<4>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
+					else if(NHK >= 4 && hint > 2u*CT) r = cta_window<3>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
 					else if(NHK >= 2 && hint > (uint32_t)CT) r = cta_window<2>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
 					else r = cta_window<1>(io, rg, sh, R, nseg, issued, ready, cler, start, end, popargs);
 					hint = cler - before;

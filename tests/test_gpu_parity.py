@@ -184,7 +184,7 @@ def test_tarta():
             _same("tarta/" + k, got[k], w)
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "split0", "split1", "deltacta", "deltaseq", "deltawarp", "tunseq", "unpackchain", "overlap1", "adjagg1"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4", "split0", "split1", "deltacta", "deltaseq", "deltawarp", "tunseq", "unpackchain", "overlap1", "overlap2", "overlap3", "adjagg1"])
 def test_alternative_clers_machines(mode, tmp_path):
     """CORTO_CLERS=1 (single-warp lazy-front machine), =2 / =3 (leader/follower without / with window steps for every mesh) and =4
     (the CTA machine for every mesh, irregular ones included; the default hands those to the leader/follower kernel) stay
