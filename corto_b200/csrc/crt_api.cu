@@ -636,16 +636,16 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
 	st += b->t_tun.size();
 	if((rc = mark(b, "tun_decode", k, s))) return rc;
-	// Stage order inside one batch (CORTO_OVERLAP, two bits; stage timers — profiling — always run serial):
-	//   bit 0  the attribute unpack beside the CLERS automaton on a side stream.  The automaton leaves most issue slots idle, but the
-	//          company costs it about what it saves on configs[1] (7.76 vs 7.77 ms; round 1, two warps per mesh: 13.1 vs 11.7 ms);
-	//          it pays on configs[3], where CLERS is long (27.0 -> 24.0 ms with both bits).  Off by default.
-	//   bit 1  the delta inverse of everything a normal estimation does NOT wait for (uv, colours, ...) on the side stream beside
-	//          the adjacency build + estimation, which are HBM-bound and leave issue slots: configs[1] 7.76 -> 7.38 ms.  ON by default.
-	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 3 : 2; }
+	// Stage order inside one batch (CORTO_OVERLAP, two bits, default 3; stage timers — profiling — always run serial, 0 = one stream):
+	//   bit 0  the attribute unpack beside the CLERS automaton on a side stream (the automaton leaves most issue slots idle).
+	//   bit 1  what an ESTIMATED / BORDER normal does not wait for leaves the critical path CLERS -> position delta -> face normals
+	//          -> estimation: the adjacency (it needs the faces, not the positions), the boundary scan and the delta inverse of the
+	//          other attributes run on the side stream beside the position delta; the dequantisation beside the estimation.
+	//   configs[1]: 7.92 (0) -> 7.08 (2) -> 6.95 ms (3); configs[3]: 27.0 -> 26.4 -> 25.2 ms.
+	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 3 : 3; }
 	const bool ovl = (b->overlap & 1) && !b->profiling && !b->clers_order.empty() && !b->t_bits.empty();
 	// bit 1: the delta inverse of everything a normal estimation does NOT wait for (uv, colours, ...) runs beside the estimation
-	const bool ovl2 = (b->overlap & 2) && !b->profiling && !b->t_faces.empty() && b->n_delta_crit > 0 && b->n_delta_crit < b->w_delta.size();
+	const bool ovl2 = (b->overlap & 2) && !b->profiling && !b->t_faces.empty() && b->n_delta_crit > 0;
 	cudaStream_t s2 = s;
 	if(ovl || ovl2) {
 		if(!b->side) {
@@ -680,21 +680,35 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 		CU(cudaEventRecord(b->ev_fork[1], s));
 		CU(cudaStreamWaitEvent(b->side, b->ev_fork[1], 0));
 		RUN(launch_delta_mesh(B, wd, (uint32_t)b->n_delta_crit, b->delta_split, s), true);
+		// side stream: the adjacency (faces only — no position is read) and the boundary scan, then the rest of the delta inverse
+		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), 1, b->side), true);
+		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, b->side), b->any_border);
 		RUN(launch_delta_mesh(B, wd + b->n_delta_crit, (uint32_t)(b->w_delta.size() - b->n_delta_crit), b->delta_split, b->side), true);
 	} else
 	RUN(launch_delta_mesh(B, (const uint2 *)(b->d_tables + b->o_w_delta), (uint32_t)b->w_delta.size(), b->delta_split, s), !b->w_delta.empty());
 	if((rc = mark(b, "delta", k, s))) return rc;
 	if(!b->t_faces.empty()) {                      // (the adjacency build reads the delta-decoded positions: it cannot move in front of the delta inverse)
-		RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), s), true);
-		RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
+		if(ovl2) {
+			RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), 2, s), true);      // face normals: the positions are final now
+			CU(cudaEventRecord(b->ev_join[1], b->side));
+			CU(cudaStreamWaitEvent(s, b->ev_join[1], 0));                                    // adjacency + boundary scan (+ the other attributes' delta)
+			// the estimation reads face normals + adjacency, not the positions: the dequantisation (which turns the integer positions
+			// into floats in place) runs beside it on the side stream, after the face normals have read them
+			CU(cudaEventRecord(b->ev_fork[0], s));
+			CU(cudaStreamWaitEvent(b->side, b->ev_fork[0], 0));
+			RUN(launch_dequant(B, t_dequant, (uint32_t)b->t_dequant.size(), b->side), !b->t_dequant.empty());
+		} else {
+			RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), 0, s), true);
+			RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
+		}
 		st += b->t_vscan.size();
 		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
 	}
-	if(ovl2) {
-		CU(cudaEventRecord(b->ev_join[1], b->side));
-		CU(cudaStreamWaitEvent(s, b->ev_join[1], 0));
-	}
 	if((rc = mark(b, "normals", k, s))) return rc;
+	if(ovl2) {
+		CU(cudaEventRecord(b->ev_join[0], b->side));
+		CU(cudaStreamWaitEvent(s, b->ev_join[0], 0));
+	} else
 	RUN(launch_dequant(B, t_dequant, (uint32_t)b->t_dequant.size(), s), !b->t_dequant.empty());
 	if((rc = mark(b, "dequant", k, s))) return rc;
 #undef RUN

@@ -1562,7 +1562,9 @@ __device__ __forceinline__ void load_face(const MeshDesc *M, uint32_t f, uint32_
 //   * slot allocation in the per-vertex adjacency: one atomicAdd per face corner.  AGG (CORTO_ADJ_AGG=1) merges the lanes of a
 //     warp that name the same vertex in the same corner (match.any) into one atomic per group; it halves the atomics of a
 //     strip but the match + shuffle chain costs more than it saves on B200 (62 -> 92 us on 16 meshes), so it is off by default.
-template <bool AGG>
+// PART: 0 both halves in one pass; 1 the adjacency only (needs the faces, not the positions: it can run BESIDE the delta inverse);
+//       2 the face normals only (needs the delta-decoded positions).
+template <bool AGG, int PART>
 __global__ void __launch_bounds__(256) k_adj_build(DevBatch B, const Tile *tiles, uint32_t ntiles) {
 	const Tile tl = tiles[blockIdx.x];
 	const MeshDesc *M = B.mesh + tl.a;
@@ -1580,12 +1582,13 @@ __global__ void __launch_bounds__(256) k_adj_build(DevBatch B, const Tile *tiles
 			load_face(M, f, v[0], v[1], v[2]);
 			valid = v[0] < M->nvert && v[1] < M->nvert && v[2] < M->nvert;
 		}
-		if(valid) {
+		if(valid && PART != 1) {
 			const float v0x = i2f(P[(size_t)v[0]*3]), v0y = i2f(P[(size_t)v[0]*3 + 1]), v0z = i2f(P[(size_t)v[0]*3 + 2]);
 			const float ax = f_sub(i2f(P[(size_t)v[1]*3]), v0x), ay = f_sub(i2f(P[(size_t)v[1]*3 + 1]), v0y), az = f_sub(i2f(P[(size_t)v[1]*3 + 2]), v0z);
 			const float bx = f_sub(i2f(P[(size_t)v[2]*3]), v0x), by = f_sub(i2f(P[(size_t)v[2]*3 + 1]), v0y), bz = f_sub(i2f(P[(size_t)v[2]*3 + 2]), v0z);
 			C.fn[f] = make_float4(f_sub(f_mul(ay, bz), f_mul(az, by)), f_sub(f_mul(az, bx), f_mul(ax, bz)), f_sub(f_mul(ax, by), f_mul(ay, bx)), 0.f);   // point.h:113-115
 		}
+		if constexpr(PART != 2) {
 #pragma unroll
 		for(int k = 0; k < 3; k++) {
 			uint32_t s = 0;
@@ -1605,6 +1608,7 @@ __global__ void __launch_bounds__(256) k_adj_build(DevBatch B, const Tile *tiles
 			}
 		}
 		if(border && valid) { atomicXor(C.bnd + v[0], v[1] ^ v[2]); atomicXor(C.bnd + v[1], v[2] ^ v[0]); atomicXor(C.bnd + v[2], v[0] ^ v[1]); }   // markBoundary :24-37
+		}
 	}
 }
 
@@ -1675,24 +1679,29 @@ __device__ __noinline__ void high_valence_normal(const MeshDesc *M, const AdjVie
 	}
 }
 
-// one thread per vertex; tiles: a = mesh, tile = block of SCAN_TILE vertices
+// one thread per vertex; tiles: a = mesh, tile = block of SCAN_TILE vertices.  Two launches of the same body: HV = false does every
+// vertex of valence <= 8 (all of a regular mesh) and nothing else — no local list, no call in its code; HV = true, right behind
+// it, does the others (its CTAs leave at once when the mesh has no overflow entry).
+template <bool HV>
 __global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile *tiles, uint32_t ntiles) {
 	const Tile tl = tiles[blockIdx.x];
 	const MeshDesc *M = B.mesh + tl.a;
 	if(B.status[tl.a]) return;
 	const AdjView C = adj_view(M);
+	if(HV && *C.novf == 0u) return;
 	const AttrDesc *A = &M->attr[M->normal_attr];
 	const int32_t *diffs = (const int32_t *)A->work_ptr;
 	const int unit = f2i_x86(A->q);
 	const bool border = A->prediction == N_BORDER;
 	for(uint32_t i = tl.tile*SCAN_TILE + threadIdx.x; i < min(M->nvert, (tl.tile + 1)*SCAN_TILE); i += 256) {
 		const uint32_t deg = C.cnt[i];
+		if((deg > 8) != HV) continue;
 		float ex = 0.f, ey = 0.f, ez = 0.f;
 		auto add_face = [&](uint32_t f) {                              // estimateNormals :44-55, one corner's worth (cross product: k_adj_build)
 			const float4 n = C.fn[f];
 			ex = f_add(ex, n.x); ey = f_add(ey, n.y); ez = f_add(ez, n.z);
 		};
-		if(deg <= 8) {
+		if constexpr(!HV) {
 			// the usual case: sort the (at most 8) incident faces in registers, add in ascending face order
 			const uint4 q0 = *(const uint4 *)(C.adj8 + (size_t)i*8), q1 = *(const uint4 *)(C.adj8 + (size_t)i*8 + 4);
 			uint32_t f0 = deg > 0 ? q0.x : 0xffffffffu, f1 = deg > 1 ? q0.y : 0xffffffffu, f2 = deg > 2 ? q0.z : 0xffffffffu, f3 = deg > 3 ? q0.w : 0xffffffffu;
@@ -1715,7 +1724,8 @@ __global__ void __launch_bounds__(256) k_normal_estimate(DevBatch B, const Tile 
 			if(deg > 6) add_face(f6);
 			if(deg > 7) add_face(f7);
 		} else {
-			high_valence_normal(M, C, i, deg, ex, ey, ez);            // out of line: keeps its local list out of the usual case's registers
+			(void)add_face;
+			high_valence_normal(M, C, i, deg, ex, ey, ez);
 		}
 		if(!border || C.bnd[i] != 0u) {                               // computeNormals :288-293 / :315-319
 			int32_t qx, qy;
@@ -2167,12 +2177,14 @@ int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, bool
 	else k_delta_mesh_cta<<<nwork, 256, 0, s>>>(B, work, nwork, mode == 2);
 	LAUNCH_CHECK(); return 0;
 }
-int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
+int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, int part, cudaStream_t s) {
 	if(ntiles == 0) return 0;
 	static int agg = -1;
 	if(agg < 0) { const char *e = getenv("CORTO_ADJ_AGG"); agg = (e && e[0] == '1') ? 1 : 0; }
-	if(agg) k_adj_build<true><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
-	else k_adj_build<false><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	if(part == 1) { if(agg) k_adj_build<true, 1><<<ntiles, 256, 0, s>>>(B, tiles, ntiles); else k_adj_build<false, 1><<<ntiles, 256, 0, s>>>(B, tiles, ntiles); }
+	else if(part == 2) k_adj_build<false, 2><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	else if(agg) k_adj_build<true, 0><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	else k_adj_build<false, 0><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {
@@ -2182,7 +2194,8 @@ int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint6
 }
 int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s) {
 	if(ntiles == 0) return 0;
-	k_normal_estimate<<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	k_normal_estimate<false><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
+	k_normal_estimate<true><<<ntiles, 256, 0, s>>>(B, tiles, ntiles);
 	LAUNCH_CHECK(); return 0;
 }
 int launch_cloud_fused(const DevBatch &B, const Tile *tiles, uint32_t ntiles, const uint32_t *heads, uint32_t nchains, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s) {

@@ -34,7 +34,7 @@ int launch_mesh_unpack(const DevBatch &B, const Tile *tiles, uint32_t ntiles, co
 int launch_clers(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, cudaStream_t s);
 int launch_clers_cta(const DevBatch &B, const uint32_t *order, uint32_t nwork, const ClersScratch &scratch, uint32_t *ticket, int sms, bool defer, cudaStream_t s);
 int launch_delta_mesh(const DevBatch &B, const uint2 *work, uint32_t nwork, bool split, cudaStream_t s);
-int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
+int launch_adj_build(const DevBatch &B, const Tile *tiles, uint32_t ntiles, int part, cudaStream_t s);
 int launch_scan_u32(const DevBatch &B, const Tile *tiles, uint32_t ntiles, uint64_t *states, uint32_t *ticket, int sms, cudaStream_t s);
 int launch_normal_estimate(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
 int launch_dequant(const DevBatch &B, const Tile *tiles, uint32_t ntiles, cudaStream_t s);
