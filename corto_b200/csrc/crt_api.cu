@@ -636,13 +636,15 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 	RUN(launch_tun_decode(B, t_tun, (uint32_t)b->t_tun.size(), st, tickets + 0, b->sms, s), !b->t_tun.empty());
 	st += b->t_tun.size();
 	if((rc = mark(b, "tun_decode", k, s))) return rc;
-	// Stage order inside one batch (CORTO_OVERLAP, two bits, default 3; stage timers — profiling — always run serial, 0 = one stream):
+	// Stage order inside one batch (CORTO_OVERLAP, three bits, default 3; stage timers — profiling — always run serial, 0 = one stream):
 	//   bit 0  the attribute unpack beside the CLERS automaton on a side stream (the automaton leaves most issue slots idle).
 	//   bit 1  what an ESTIMATED / BORDER normal does not wait for leaves the critical path CLERS -> position delta -> face normals
 	//          -> estimation: the adjacency (it needs the faces, not the positions), the boundary scan and the delta inverse of the
-	//          other attributes run on the side stream beside the position delta; the dequantisation beside the estimation.
-	//   configs[1]: 7.92 (0) -> 7.08 (2) -> 6.95 ms (3); configs[3]: 27.0 -> 26.4 -> 25.2 ms.
-	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 3 : 3; }
+	//          other attributes run on the side stream beside the position delta.
+	//   bit 2  the dequantisation beside the estimation (which reads face normals + adjacency, not the positions).  Both are
+	//          HBM-bound: no gain, noisier (6.73 / 7.19 ms in two runs) — off by default.
+	//   configs[1] on one box: 7.57 (0) -> 6.90 (2) -> 6.74 ms (3); configs[3]: 27.0 -> 26.4 -> 25.2 ms.
+	if(b->overlap < 0) { const char *e = getenv("CORTO_OVERLAP"); b->overlap = e ? atoi(e) & 7 : 3; }
 	const bool ovl = (b->overlap & 1) && !b->profiling && !b->clers_order.empty() && !b->t_bits.empty();
 	// bit 1: the delta inverse of everything a normal estimation does NOT wait for (uv, colours, ...) runs beside the estimation
 	const bool ovl2 = (b->overlap & 2) && !b->profiling && !b->t_faces.empty() && b->n_delta_crit > 0;
@@ -694,9 +696,11 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 			CU(cudaStreamWaitEvent(s, b->ev_join[1], 0));                                    // adjacency + boundary scan (+ the other attributes' delta)
 			// the estimation reads face normals + adjacency, not the positions: the dequantisation (which turns the integer positions
 			// into floats in place) runs beside it on the side stream, after the face normals have read them
-			CU(cudaEventRecord(b->ev_fork[0], s));
-			CU(cudaStreamWaitEvent(b->side, b->ev_fork[0], 0));
-			RUN(launch_dequant(B, t_dequant, (uint32_t)b->t_dequant.size(), b->side), !b->t_dequant.empty());
+			if(b->overlap & 4) {
+				CU(cudaEventRecord(b->ev_fork[0], s));
+				CU(cudaStreamWaitEvent(b->side, b->ev_fork[0], 0));
+				RUN(launch_dequant(B, t_dequant, (uint32_t)b->t_dequant.size(), b->side), !b->t_dequant.empty());
+			}
 		} else {
 			RUN(launch_adj_build(B, t_faces, (uint32_t)b->t_faces.size(), 0, s), true);
 			RUN(launch_scan_u32(B, t_vscan, (uint32_t)b->t_vscan.size(), st, tickets + 4, b->sms, s), b->any_border);
@@ -705,7 +709,7 @@ extern "C" int crt_batch_decode(crt_batch *b, void *stream_) {
 		RUN(launch_normal_estimate(B, t_verts, (uint32_t)b->t_verts.size(), s), true);
 	}
 	if((rc = mark(b, "normals", k, s))) return rc;
-	if(ovl2) {
+	if(ovl2 && (b->overlap & 4)) {
 		CU(cudaEventRecord(b->ev_join[0], b->side));
 		CU(cudaStreamWaitEvent(s, b->ev_join[0], 0));
 	} else
