@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,56 @@ extern "C" int crt_device_available(void) {
 }
 
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1)/a*a; }
+
+// Small device blocks are recycled instead of going back to the driver: a crt::Decoder-shaped call (one mesh, host buffers)
+// would otherwise spend more time in cudaMalloc / cudaFree (implicit device syncs) than in its kernels.  Blocks up to 64 MB,
+// at most 512 MB held per process, keyed by device; anything larger is a plain cudaMalloc / cudaFree.  A block returns here only
+// after the work that used it has completed (crt_decode synchronises; batch_free_device synchronises the device first).
+namespace {
+struct DevCache {
+	std::mutex m;
+	std::multimap<std::pair<int, size_t>, void *> free_blocks;
+	std::map<void *, std::pair<int, size_t>> live;
+	size_t held = 0;
+};
+DevCache g_dev_cache;
+constexpr size_t DEV_CACHE_BLOCK = 64ull << 20, DEV_CACHE_TOTAL = 512ull << 20;
+cudaError_t dev_alloc(void **p, size_t n) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if(n <= DEV_CACHE_BLOCK) {
+		std::lock_guard<std::mutex> g(g_dev_cache.m);
+		auto it = g_dev_cache.free_blocks.lower_bound({dev, n});
+		if(it != g_dev_cache.free_blocks.end() && it->first.first == dev && it->first.second <= 2*n + 65536) {
+			*p = it->second;
+			g_dev_cache.live[*p] = it->first;
+			g_dev_cache.held -= it->first.second;
+			g_dev_cache.free_blocks.erase(it);
+			return cudaSuccess;
+		}
+	}
+	cudaError_t e = cudaMalloc(p, n);
+	if(e == cudaSuccess && n <= DEV_CACHE_BLOCK) { std::lock_guard<std::mutex> g(g_dev_cache.m); g_dev_cache.live[*p] = {dev, n}; }
+	return e;
+}
+void dev_free(void *p) {
+	if(!p) return;
+	{
+		std::lock_guard<std::mutex> g(g_dev_cache.m);
+		auto it = g_dev_cache.live.find(p);
+		if(it != g_dev_cache.live.end()) {
+			const std::pair<int, size_t> key = it->second;
+			g_dev_cache.live.erase(it);
+			if(g_dev_cache.held + key.second <= DEV_CACHE_TOTAL) {
+				cudaDeviceSynchronize();                   // what cudaFree would have implied: nothing in flight may still touch the block
+				g_dev_cache.free_blocks.insert({key, p}); g_dev_cache.held += key.second;
+				return;
+			}
+		}
+	}
+	cudaFree(p);
+}
+}  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
 struct Binding { void *ptr; int format; int components; };
@@ -156,10 +207,11 @@ extern "C" crt_batch *crt_batch_create_device(int n, const unsigned char *const 
 }
 
 static void batch_free_device(crt_batch *b) {
-	if(b->d_blobs && !b->blobs_external) cudaFree(b->d_blobs);
-	if(b->d_tables) cudaFree(b->d_tables);
-	if(b->d_scratch) cudaFree(b->d_scratch);
-	if(b->d_zero) cudaFree(b->d_zero);
+	if(b->d_tables || b->d_scratch || b->d_zero) cudaDeviceSynchronize();   // (cudaFree used to imply it; recycled blocks must be idle)
+	if(b->d_blobs && !b->blobs_external) dev_free(b->d_blobs);
+	if(b->d_tables) dev_free(b->d_tables);
+	if(b->d_scratch) dev_free(b->d_scratch);
+	if(b->d_zero) dev_free(b->d_zero);
 	if(!b->blobs_external) b->d_blobs = nullptr;
 	b->d_tables = b->d_scratch = b->d_zero = nullptr;
 	for(auto &s: b->stages) cudaEventDestroy(s.ev);
@@ -416,8 +468,8 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	for(auto &m: b->meshes) blobs_bytes += align_up(m.len, 16);
 	if(b->blobs_external) copy_blobs = false;
 	else if(!b->d_blobs || b->blobs_bytes < blobs_bytes) {
-		if(b->d_blobs) { cudaFree(b->d_blobs); b->d_blobs = nullptr; }
-		CU(cudaMalloc(&b->d_blobs, blobs_bytes));
+		if(b->d_blobs) { dev_free(b->d_blobs); b->d_blobs = nullptr; }
+		CU(dev_alloc((void **)&b->d_blobs, blobs_bytes));
 		b->blobs_bytes = blobs_bytes;
 		copy_blobs = true;
 	}
@@ -442,8 +494,8 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	         o_rec = align_up(o_adj + adj_bytes, 256), o_used = align_up(o_rec + ntun*TUN_REC_BYTES, 256),
 	         o_clers = align_up(o_used + ntun*4 + 16, 256), total = o_clers + per_slot*slots + 256;
 	if(!b->d_scratch || b->scratch_bytes < total) {
-		if(b->d_scratch) { cudaFree(b->d_scratch); b->d_scratch = nullptr; }
-		CU(cudaMalloc(&b->d_scratch, total));
+		if(b->d_scratch) { dev_free(b->d_scratch); b->d_scratch = nullptr; }
+		CU(dev_alloc((void **)&b->d_scratch, total));
 		b->scratch_bytes = total;
 	}
 	b->d_symbols = b->d_scratch + o_sym;
@@ -467,8 +519,8 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->z_csr = align_up(b->z_tunbits + ntun*8, 256);
 	uint64_t zero_total = b->z_csr + csr_bytes + 256;
 	if(!b->d_zero || b->zero_bytes < zero_total) {
-		if(b->d_zero) { cudaFree(b->d_zero); b->d_zero = nullptr; }
-		CU(cudaMalloc(&b->d_zero, zero_total));
+		if(b->d_zero) { dev_free(b->d_zero); b->d_zero = nullptr; }
+		CU(dev_alloc((void **)&b->d_zero, zero_total));
 	}
 	b->zero_bytes = zero_total;
 
@@ -539,8 +591,8 @@ static int batch_prepare(crt_batch *b, cudaStream_t stream, bool copy_blobs) {
 	b->c_cfused.push_back((uint32_t)b->t_cfused.size());
 	b->o_c_cfused = put(img, b->c_cfused);
 	if(!b->d_tables || b->tables_bytes < img.size()) {
-		if(b->d_tables) { cudaFree(b->d_tables); b->d_tables = nullptr; }
-		CU(cudaMalloc(&b->d_tables, img.size() + 256));
+		if(b->d_tables) { dev_free(b->d_tables); b->d_tables = nullptr; }
+		CU(dev_alloc((void **)&b->d_tables, img.size() + 256));
 		b->tables_bytes = img.size() + 256;
 	}
 	CU(cudaMemcpyAsync(b->d_tables, img.data(), img.size(), cudaMemcpyHostToDevice, stream));
@@ -885,7 +937,7 @@ extern "C" int crt_decode(crt_decoder *d) {
 	struct Out { void *dev; void *host; size_t bytes; };
 	std::vector<Out> outs;
 	int rc = CRT_OK;
-	auto cleanup = [&]() { for(auto &o: outs) cudaFree(o.dev); crt_batch_destroy(b); };
+	auto cleanup = [&]() { for(auto &o: outs) dev_free(o.dev); crt_batch_destroy(b); };
 	for(size_t a = 0; a < pm.attrs.size() && rc == CRT_OK; a++) {
 		const ParsedAttr &pa = pm.attrs[a];
 		if(pa.codec == CODEC_NORMAL) d->normal_prediction = pm.streams[a].prediction;
@@ -898,18 +950,19 @@ extern "C" int crt_decode(crt_decoder *d) {
 		else if(pa.codec == CODEC_COLOR) stride = (size_t)hb.components;
 		else stride = (size_t)pa.N*4;
 		Out o{nullptr, hb.ptr, stride*pm.nvert};
-		cudaError_t e = cudaMalloc(&o.dev, o.bytes + 16);
+		cudaError_t e = dev_alloc((void **)&o.dev, o.bytes + 16);
 		if(e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(output)"); break; }
 		outs.push_back(o);
 		// the caller's buffer content is preserved where the reference leaves elements untouched
 		if(pa.codec == CODEC_NORMAL && hb.format == CRT_INT16) cudaMemcpy(o.dev, o.host, o.bytes, cudaMemcpyHostToDevice);
+		else cudaMemsetAsync(o.dev, 0, o.bytes, nullptr);   // elements no kernel writes (a stream shorter than nvert) come back as 0, never as stale device memory
 		rc = crt_batch_bind(b, pa.name.c_str(), o.dev, hb.format, hb.components);
 	}
 	if(rc == CRT_OK && pm.nface && d->index) {
 		Out o{nullptr, d->index, (size_t)pm.nface*3*(d->index16 ? 2 : 4)};
-		cudaError_t e = cudaMalloc(&o.dev, o.bytes + 16);
+		cudaError_t e = dev_alloc((void **)&o.dev, o.bytes + 16);
 		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(index)");
-		else { outs.push_back(o); rc = crt_batch_bind(b, "index", o.dev, d->index16 ? CRT_UINT16 : CRT_UINT32, 0); }
+		else { outs.push_back(o); cudaMemsetAsync(o.dev, 0, o.bytes, nullptr); rc = crt_batch_bind(b, "index", o.dev, d->index16 ? CRT_UINT16 : CRT_UINT32, 0); }   // (faces past the last group end: 0)
 	}
 	if(rc == CRT_OK) rc = crt_batch_upload(b, nullptr);
 	if(rc == CRT_OK) rc = crt_batch_decode(b, nullptr);
