@@ -7,9 +7,9 @@ mkdir -p $O
 timeout 2000 python -X faulthandler -m pytest tests -m gpu -x -q -p no:cacheprovider > $O/r2h_pytest_gpu.txt 2>&1
 echo "pytest rc=$?" >> $O/r2h_pytest_gpu.txt
 grep -v "^  File" $O/r2h_pytest_gpu.txt | tail -30
-timeout 900 compute-sanitizer --tool synccheck --print-limit 10 python scratch/c4dbg.py 320 > $O/r2h_synccheck.txt 2>&1
+timeout 900 compute-sanitizer --tool synccheck --print-limit 10 python profiles/c4_batch_320.py 320 > $O/r2h_synccheck.txt 2>&1
 grep -v "Host Frame" $O/r2h_synccheck.txt | tail -12 | cut -c1-250
-timeout 1500 compute-sanitizer --tool racecheck --print-limit 30 python scratch/c4dbg.py 320 > $O/r2h_racecheck.txt 2>&1
+timeout 1500 compute-sanitizer --tool racecheck --print-limit 30 python profiles/c4_batch_320.py 320 > $O/r2h_racecheck.txt 2>&1
 grep -v "Host Frame" $O/r2h_racecheck.txt | tail -30 | cut -c1-250
 for w in c2 c5 tarta c4; do
   extra=""; [ $w = c2 ] && extra="--distinct 16"; [ $w = c4 ] && extra="--distinct 64"

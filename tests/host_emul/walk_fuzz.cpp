@@ -24,6 +24,35 @@ static int try_blob(const uint8_t *src, size_t n) {
 	return rc;
 }
 
+// The same walk REPLAYED from a tape (crt_walk.cpp: Cur, replay mode — how a rank that holds the blob in device memory only gets
+// its directory): the tape is in a heap buffer of exactly its size, the blob pointer is null.
+static int try_tape(const uint8_t *tape, size_t tn, size_t blob_len, crtb::ParsedMesh *out = nullptr) {
+	uint8_t *buf = (uint8_t *)malloc(tn ? tn : 1);
+	memcpy(buf, tape, tn);
+	crtb::ParsedMesh m;
+	m.tape = buf; m.tape_len = (uint32_t)tn;
+	std::string err;
+	int rc = crtb::parse_header(nullptr, (int)blob_len, m, err);
+	if(rc == 0) rc = crtb::walk_directory(m, err);
+	if(out && rc == 0) { *out = m; out->tape = nullptr; }
+	free(buf);
+	return rc;
+}
+
+static bool same_directory(const crtb::ParsedMesh &a, const crtb::ParsedMesh &b) {
+	if(a.nvert != b.nvert || a.nface != b.nface || a.max_front != b.max_front || a.split_off != b.split_off || a.split_nwords != b.split_nwords) return false;
+	if(a.group_ends != b.group_ends || a.group_props != b.group_props || a.exif != b.exif || a.streams.size() != b.streams.size()) return false;
+	if(a.clers.data_off != b.clers.data_off || a.clers.csize != b.clers.csize || a.clers.size != b.clers.size) return false;
+	for(size_t i = 0; i < a.streams.size(); i++) {
+		const crtb::AttrStreams &x = a.streams[i], &y = b.streams[i];
+		if(x.bits_off != y.bits_off || x.bits_nwords != y.bits_nwords || x.prediction != y.prediction || x.blocks.size() != y.blocks.size()) return false;
+		for(size_t k = 0; k < x.blocks.size(); k++)
+			if(x.blocks[k].data_off != y.blocks[k].data_off || x.blocks[k].csize != y.blocks[k].csize || x.blocks[k].size != y.blocks[k].size ||
+			   x.blocks[k].probs_off != y.blocks[k].probs_off || x.blocks[k].nsym != y.blocks[k].nsym) return false;
+	}
+	return true;
+}
+
 int main(int argc, char **argv) {
 	if(argc < 3) return 2;
 	FILE *f = fopen(argv[1], "rb");
@@ -51,6 +80,26 @@ int main(int argc, char **argv) {
 			bad[pos] = how == 0 ? 0x00 : how == 1 ? 0xFF : (uint8_t)rnd();
 		}
 		if(try_blob(bad.data(), n) == 0) accepted++; else rejected++;
+	}
+	// ---- walk tapes: record on the intact blob, replay without it; truncated and edited tapes must fail or stay in bounds
+	{
+		crtb::ParsedMesh direct, replayed;
+		std::vector<uint8_t> tape;
+		std::string err;
+		direct.record = &tape;
+		if(crtb::parse_header(blob.data(), (int)n, direct, err) || crtb::walk_directory(direct, err)) { fprintf(stderr, "recording walk failed\n"); return 1; }
+		if(try_tape(tape.data(), tape.size(), n, &replayed) != 0 || !same_directory(direct, replayed)) { fprintf(stderr, "tape replay differs from the direct walk\n"); return 1; }
+		for(size_t cut = 0; cut < tape.size(); cut++)
+			if(try_tape(tape.data(), cut, n) == 0) { fprintf(stderr, "tape truncated at %zu of %zu accepted\n", cut, tape.size()); return 1; }
+		long tacc = 0, trej = 0;
+		std::vector<uint8_t> bt;
+		for(int t = 0; t < trials; t++) {
+			bt = tape;
+			const int edits = 1 + (int)(rnd() % 3);
+			for(int e = 0; e < edits; e++) { const uint32_t how = rnd() % 4; bt[rnd() % bt.size()] = how == 0 ? 0x00 : how == 1 ? 0xFF : (uint8_t)rnd(); }
+			if(try_tape(bt.data(), bt.size(), (rnd() & 1) ? n : (size_t)(rnd() % (n + 1))) == 0) tacc++; else trej++;
+		}
+		printf("tape %zu bytes: accepted %ld rejected %ld\n", tape.size(), tacc, trej);
 	}
 	printf("accepted %ld rejected %ld\n", accepted, rejected);
 	return 0;

@@ -174,7 +174,9 @@ def test_mutated_directories_never_escape_the_blob(name):
 
 def test_walk_under_sanitizers(tmp_path):
     """crt_walk.cpp under AddressSanitizer + UBSan: every truncation and 3000 random edits per fixture, each in a heap buffer of
-    exactly the blob's size (tests/host_emul/walk_fuzz.cpp).  Any out-of-bounds read aborts the run."""
+    exactly the blob's size (tests/host_emul/walk_fuzz.cpp).  Any out-of-bounds read aborts the run.  The same for the walk REPLAYED
+    from a tape (no blob: crt_batch_create_device): the replay equals the direct walk, every truncated tape is refused, 3000 edited
+    tapes stay in bounds."""
     exe = str(tmp_path / "walk_fuzz")
     src = [os.path.join(ROOT, "tests", "host_emul", "walk_fuzz.cpp"), os.path.join(ROOT, "corto_b200", "csrc", "crt_walk.cpp")]
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", os.path.join(ROOT, "include"),
