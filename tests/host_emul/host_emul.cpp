@@ -225,6 +225,118 @@ int emul_walk_blocks(const uint8_t *blob, int len, uint32_t *out, int cap) {
 
 // CLERS automaton through clers_decode_seq given the decoded cler bytes (from the oracle); outputs faces (u32)
 // and prediction (3 u32 per vertex).  Returns the automaton's return code.
+// ---- host transcriptions of the CURRENT CTA-wide steps (k_clers_cta v7.3, crt_clers_cta.cu): windows of any width take runs of
+// >= 1 symbols, verify consecutive prev chains in the ring OR in the reach-back store, RETIRE the gate when the symbol after the
+// run is BOUNDARY / DELAY and hand over to the pop; the pop CONSUMES a BOUNDARY / DELAY waiting on the popped edge and scans on.
+// Returns 1 when the gate was retired (pop next), else 0; `progress` = symbols consumed.
+static int cta_window2_host(const ClersIO &io, ArrayRings &rg, MergedState &S, uint32_t W, uint32_t R, bool &bail) {
+	bail = false;
+	uint32_t done = 0;
+	for(;;) {
+		const uint32_t cler = S.cler, start = S.start, end = S.end;
+		const uint32_t lim = std::min(W, std::min(io.nclers - cler, end - start));
+		uint32_t m = 0;
+		while(m < lim && rg.sym(cler + m) <= (uint32_t)C_LEFT) m++;
+		std::vector<uint32_t> nVb(m + 1, 0), nLb(m + 1, 0);
+		for(uint32_t j = 0; j < m; j++) { nVb[j + 1] = nVb[j] + (rg.sym(cler + j) == C_VERTEX); nLb[j + 1] = nLb[j] + (rg.sym(cler + j) == C_LEFT); }
+		const uint32_t nV = nVb[m], nL = nLb[m];
+		const uint32_t prev = S.prev, next = S.next, nfront = S.nfront, vcount = S.vcount, eflush = S.eflush, ndel = S.ndel;
+		if(m < 1 || nfront + nV + 1 > io.cap || vcount + nV > io.nvert) { bail = done == 0; return 0; }
+		if(nfront + nV + 1 > eflush + R) return 0;                       // the caller writes ring entries back first
+		auto loadB = [&](uint32_t id, uint32_t &p, uint32_t &n) { if(id >= eflush) rg.ldB(id, p, n); else { p = io.eb[id].prev; n = io.eb[id].next; } };
+		auto loadA0 = [&](uint32_t id) { uint32_t a, t1, t2; if(id >= eflush) { rg.ldA(id, a, t1, t2); return a; } return io.ea[id].v0; };
+		std::vector<uint32_t> chain(nL + 1);
+		bool fast = true;
+		for(uint32_t k = 0; k < nL && fast; k++) {                        // consecutive ids, in the ring or in the reach-back store
+			const uint32_t id = prev + k;
+			if(!(id < nfront && id != next)) { fast = false; break; }
+			uint32_t pk, pn; loadB(id, pk, pn);
+			chain[k] = id;
+			if(k + 1 == nL) chain[nL] = pk; else if(pk != id + 1) fast = false;
+		}
+		if(nL == 0) chain[0] = prev;
+		if(!fast) {
+			uint32_t q = prev; bool ok = true;
+			for(uint32_t k = 0; k < nL; k++) {
+				chain[k] = q;
+				if(q == next || q >= nfront) { ok = false; break; }
+				uint32_t pp, pq; loadB(q, pp, pq); q = pp;
+			}
+			chain[nL] = q;
+			if(!ok) { bail = done == 0; return 0; }
+		}
+		std::vector<uint32_t> aL(nL + 1, 0);
+		for(uint32_t k = 0; k < nL; k++) aL[k] = loadA0(chain[k]);
+		// the symbol after the run
+		const uint32_t newprev = chain[nL], nextf = nV ? nfront + nV - 1 : next, gid = nfront + nV;
+		uint32_t cm = 0xff;
+		if(cler + m < io.nclers && start + m < end) cm = rg.sym(cler + m);
+		const bool gend = (cm == C_BOUNDARY || (cm == C_DELAY && ndel < io.cap)) && newprev != nextf && newprev < nfront;
+		uint32_t e_v0 = S.v0, e_v1 = S.v1, e_v2 = S.v2;
+		for(uint32_t i = 0; i < m; i++) {
+			const bool isV = rg.sym(cler + i) == C_VERTEX;
+			const uint32_t rv = nVb[i], rl = nLb[i];
+			const uint32_t v0i = rl ? aL[rl - 1] : S.v0, v1i = rv ? vcount + rv - 1 : S.v1;
+			uint32_t v2i;
+			if(i == 0) v2i = S.v2;
+			else if(rg.sym(cler + i - 1) == C_VERTEX) v2i = rv > 1 ? vcount + rv - 2 : S.v1;
+			else v2i = rl > 1 ? aL[rl - 2] : S.v0;
+			const uint32_t x = vcount + rv, a = isV ? 0 : aL[rl];
+			clers_put_face(io, (size_t)(start + i)*3u, v1i, v0i, isV ? x : a);
+			if(isV) {
+				clers_put_pred(io, x, v1i, v0i, v2i);
+				const uint32_t b = nfront + rv;
+				rg.stA(b, x, v1i, v0i); rg.stB(b, rv + 1 < nV ? b + 1 : (gend ? gid : CLERS_NOLINK), rv ? b - 1 : next); rg.stFl(b, 0);
+			} else {
+				const uint32_t id = chain[rl];
+				if(id >= eflush) rg.stFl(id, CLERS_DEL); else io.fl[id] = CLERS_DEL;
+			}
+			if(i == m - 1) { e_v0 = isV ? v0i : a; e_v1 = isV ? x : v1i; e_v2 = isV ? v1i : v0i; }
+		}
+		if(gend) {                                                        // the gate gets a record and leaves the machine
+			rg.stA(gid, e_v0, e_v1, e_v2); rg.stB(gid, newprev, nextf); rg.stFl(gid, CLERS_NQ);
+			if(newprev >= eflush) rg.stB_next(newprev, gid); else io.eb[newprev].next = gid;
+			if(nV == 0) { if(next >= eflush) rg.stB_prev(next, gid); else io.eb[next].prev = gid; }
+			if(cm == C_DELAY) io.delayed[ndel] = gid;
+		}
+		if(nV) { if(next >= eflush) rg.stB_prev(next, nfront); else io.eb[next].prev = nfront; S.next = nextf; }
+		S.v0 = e_v0; S.v1 = e_v1; S.v2 = e_v2;
+		S.nfront = nfront + nV + (gend ? 1u : 0u); S.vcount = vcount + nV; S.prev = newprev;
+		S.start = start + m; S.cler = cler + m + (gend ? 1u : 0u); S.lp = S.ln = 1; S.cf = CLERS_NOID;
+		S.have = (!gend && S.start < end) ? 1u : 0u;
+		if(gend && cm == C_DELAY) S.ndel = ndel + 1;
+		done += m;
+		if(gend) return 1;
+		if(m < W || S.start >= end || S.cler >= io.nclers) return 0;
+		if(S.nfront + W + 1 > eflush + R) return 0;
+	}
+}
+
+static int cta_pop2_host(const ClersIO &io, ArrayRings &rg, MergedState &S) {
+	uint32_t found = CLERS_NOID, c = 0xff;
+	while(S.scan < S.nfront) {
+		const uint32_t id = S.scan++;
+		const uint32_t fl = id >= S.eflush ? rg.ldFl(id) : io.fl[id];
+		if(fl != 0) continue;
+		found = id;
+		c = S.cler < io.nclers ? rg.sym(S.cler) : 0xffu;
+		if(c == C_BOUNDARY || (c == C_DELAY && S.ndel < io.cap)) {        // consumed right here: the edge keeps its record
+			if(c == C_DELAY) io.delayed[S.ndel++] = found;
+			S.cler++;
+			found = CLERS_NOID;
+			continue;
+		}
+		break;
+	}
+	if(found != CLERS_NOID) {
+		uint32_t p, q, a, b, c2;
+		if(found >= S.eflush) { rg.ldB(found, p, q); rg.ldA(found, a, b, c2); }
+		else { p = io.eb[found].prev; q = io.eb[found].next; a = io.ea[found].v0; b = io.ea[found].v1; c2 = io.ea[found].v2; }
+		S.prev = p; S.next = q; S.v0 = a; S.v1 = b; S.v2 = c2; S.lp = S.ln = 0; S.have = 1; S.cf = found;
+	}
+	return found != CLERS_NOID && c <= (uint32_t)C_LEFT;
+}
+
 // ring_r == 0: clers_decode_seq; else clers_decode_ring with an R = ring_r edge ring and Q = ring_q FIFO ring (tiny rings
 // force the reach-back paths that are rare with the kernel's sizes).
 int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t nclers, uint32_t *faces, uint32_t *prediction, int ring_r, int ring_q) {
@@ -348,6 +460,35 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		MergedState S; merged_init(S);
 		int mode = 0; bool tried = false;
 		rc = 0;
+		if(getenv("EMUL_PROTO") && atoi(getenv("EMUL_PROTO")) == 2) {
+			// the CURRENT step protocol of k_clers_cta: dispatch -> (window <-> pop) cycles, everything else one scalar symbol at a time
+			const uint32_t KEEP2 = R - 2u*W, ROOM = W + 4u;
+			for(long guard = 0; guard < (1l << 40) && mode == 0; guard++) {
+				if(S.nfront + ROOM > S.eflush + R) {
+					const uint32_t e1 = (S.nfront - KEEP2) & ~3u;
+					for(uint32_t id = S.eflush; id < e1; id++) { const uint4_t a = ra[id & (R - 1)]; const uint2_t l = rb[id & (R - 1)]; ea[id] = EdgeA{a.x, a.y, a.z, 0}; eb[id] = EdgeB{l.x, l.y}; io.fl[id] = rf[id & (R - 1)]; }
+					S.eflush = e1;
+					continue;
+				}
+				const bool canpop = S.start < S.end && S.scan < S.nfront;
+				const uint32_t c0 = S.cler < io.nclers ? rg.sym(S.cler) : 0xffu;
+				int step = 2;
+				if(S.have && !tried && c0 <= (uint32_t)C_LEFT) step = 0; else if(!S.have && canpop) step = 1;
+				if(step == 2) {
+					const uint32_t c1 = S.cler, s1 = S.start, g1 = S.g, h1 = S.have, n1 = S.ndel, q1 = S.scan;
+					int r2 = clers_merged(io, rg, S, 1, false, 2u, splitbits);
+					if(r2 == 0 && c1 == S.cler && s1 == S.start && g1 == S.g && h1 == S.have && n1 == S.ndel && q1 == S.scan) r2 = -5;
+					tried = false; mode = r2;
+					continue;
+				}
+				for(;;) {
+					if(step == 0) { bool bail; const int r2 = cta_window2_host(io, rg, S, W, R, bail); tried = bail; if(!r2) break; step = 1; }
+					else { const int r2 = cta_pop2_host(io, rg, S); tried = false; if(!r2) break; step = 0; }
+				}
+			}
+			vc = S.vcount;
+			rc = mode < 0 ? mode : 0;
+		} else {
 		for(long guard = 0; guard < (1l << 40); guard++) {
 			if(mode == 1 || mode < 0) break;
 			if(S.nfront + W > S.eflush + R) {
@@ -362,6 +503,7 @@ int emul_clers(const uint8_t *blob, int len, const uint8_t *clers_in, uint32_t n
 		}
 		vc = S.vcount;
 		rc = mode < 0 ? mode : 0;
+		}
 	} else rc = -99;
 	for(uint32_t v = 0; v < pm.nvert; v++) for(int k = 0; k < 3; k++) prediction[v*3 + k] = pred[(size_t)v*4 + k];
 	return rc;

@@ -272,6 +272,52 @@ def test_merged_clers_machine_on_cpu(emul, name):
             os.environ.pop(k, None)
 
 
+def _emul_proto2(emul, blob, o, combos):
+    try:
+        os.environ["EMUL_PROTO"] = "2"
+        for W, R in combos:
+            os.environ["EMUL_W"] = str(W)
+            faces = np.zeros((o["nface"], 3), np.uint32); pred = np.zeros((o["nvert"], 3), np.uint32)
+            rc = emul.emul_clers(_p(blob), len(blob), _p(o["clers"]), len(o["clers"]), _p(faces), _p(pred), R, 0)
+            assert rc == 0 and np.array_equal(faces, o["index"]) and np.array_equal(pred[1:], o["prediction"][1:]), (W, R, rc)
+    finally:
+        for k in ("EMUL_PROTO", "EMUL_W"):
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.SMALL])
+def test_cta_step_protocol_on_cpu(emul, name):
+    """The CURRENT step protocol of k_clers_cta (crt_clers_cta.cu, v7.3) transcribed for the host — windows of any width over runs of
+    >= 1 symbols that retire the gate on BOUNDARY / DELAY, consecutive prev chains verified in the ring or in the reach-back store,
+    pops that consume BOUNDARY / DELAY, one scalar symbol (clers_merged) for the rest, write-back with the kernel's KEEP / ROOM rule —
+    against the oracle's faces + predictions, for window widths 8 .. 1024 and rings down to 32 entries."""
+    blob = _golden(name)
+    o = pyoracle.decode(blob, debug=True)
+    if not o["nface"]:
+        return
+    _emul_proto2(emul, blob, o, ((16, 64), (8, 32), (32, 128), (256, 1024), (256, 2048), (512, 2048), (1024, 4096), (1024, 8192)))
+
+
+def test_cta_step_protocol_on_cpu_large(emul):
+    """The same on a configs[1]-sized grid (256 K symbols, strips of ~700) and on the reference's real scan (3.7 M symbols, runs of ~6,
+    DELAY / RIGHT / SPLIT everywhere), with the kernel's own ring sizes."""
+    from oracle import refshim
+    done = 0
+    if refshim.available():
+        from oracle import workloads
+        blob = workloads._c2(3)
+        _emul_proto2(emul, blob, pyoracle.decode(blob, debug=True), ((1024, 4096), (512, 2048), (256, 1024)))
+        blob = workloads._c4(10)                     # a grid with a punched hole: DELAY / SPLIT / RIGHT between the strips
+        _emul_proto2(emul, blob, pyoracle.decode(blob, debug=True), ((512, 2048), (1024, 8192)))
+        done += 1
+    if os.path.exists(refshim.TARTA):
+        blob = refshim.aligned_blob(open(refshim.TARTA, "rb").read())
+        _emul_proto2(emul, blob, pyoracle.decode(blob, debug=True), ((1024, 8192), (256, 2048)))
+        done += 1
+    if not done:
+        pytest.skip("needs oracle/_ref (reference encoder, tarta.crt)")
+
+
 # ---- multi-rank sharding over gloo, world_size 2 ---------------------------------------------------------------------
 def test_shard_lpt_balances():
     rs = np.random.RandomState(1)
