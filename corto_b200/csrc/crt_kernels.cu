@@ -9,13 +9,18 @@
 // k_unpack_chain   decodeArray / decodeValues        include/corto/cstream.h:294-360  meshes: tiles of 1024 vertices, all
 // k_unpack_fused<MESH>                                                               components; bit offset = running total
 //                                                                                   per chain, or block scan + look-back
-// k_unpack_fused<CLOUD>  ... + GenericAttr::deltaDecode (cloud) vertex_attribute.h:177-181, NormalAttr::deltaDecode (cloud)
-//                  normal_attribute.cpp:202-207 + dequantize: point clouds in ONE pass
-// k_clers_lf       Decoder::decodeFaces              src/decoder.cpp:204-358        serial automaton, two warps per mesh
+// k_cloud_chain / k_unpack_fused<CLOUD>  ... + GenericAttr::deltaDecode (cloud) vertex_attribute.h:177-181, NormalAttr::deltaDecode
+//                  (cloud) normal_attribute.cpp:202-207 + dequantize: point clouds in ONE pass; one CTA per chain with both
+//                  carries in shared memory, or ticketed tiles + look-back for a few large clouds
+// k_clers_cta      Decoder::decodeFaces              src/decoder.cpp:204-358        crt_clers_cta.cu: one CTA per mesh, runs of
+//                                                                                   VERTEX / LEFT in closed form (regular streams)
+// k_clers_lf       (the same)                                                       serial automaton, two warps per mesh: the
+//                                                                                   irregular streams k_clers_cta defers
 // k_clers          (the same, single-warp variant kept as A/B baseline, CORTO_CLERS=1)
-// k_delta_mesh     GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     warp per (mesh, attribute[, component])
-//                  NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201
-// k_delta_mesh_cta (the same, one CTA per chain, 256 vertices per round; experiment switch CORTO_DELTA=cta)
+// k_delta_mesh_seg GenericAttr::deltaDecode (mesh)   vertex_attribute.h:165-176     CTA per (mesh, attribute): segmented-scan
+//                  NormalAttr::deltaDecode (mesh)    normal_attribute.cpp:193-201   rounds of 256 vertices (regular meshes);
+// k_delta_mesh     (the same)                                                       warp per (mesh, attribute[, component])
+// k_delta_mesh_cta (the same, one CTA per chain, pointer-doubling rounds; experiment switch CORTO_DELTA=cta)
 // k_adj_build / k_scan_u32 / k_normal_estimate
 //                  markBoundary, estimateNormals, computeNormals   normal_attribute.cpp:24-59, 281-325
 // k_dequant        GenericAttr::dequantize, NormalAttr::dequantize, ColorAttr::dequantize
