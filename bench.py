@@ -5,7 +5,8 @@
 
 A "step" is one pass of the decode hot path over one batch of synthetic meshes (BASELINE configs[1]: 256 x 128K-vertex
 pos14/uv12/normal10 meshes per GPU).  Work shards by mesh: every rank decodes its own batch (weak scaling), there is no
-data-path collective; torch.distributed is used only for the barrier and the max-over-ranks time.
+data-path collective inside the decode; torch.distributed carries the barrier, the max-over-ranks time and — in
+the `shard` block — the one exchange the path has: the scatter of the compressed blobs from the ingest rank.
 
   value     verts decoded by all ranks / max-over-ranks device time, blobs already resident in HBM, outputs left in HBM.
             The host directory walk (O(#blocks), microseconds per mesh) + its H2D is re-done INSIDE every timed step.
@@ -15,6 +16,11 @@ data-path collective; torch.distributed is used only for the barri
             duration (the library's CUDA-event stage timers over a re-run of the same steps right after the timed region)
             against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores, rank 0, N=1 only.
+  shard     BASELINE configs[3] as north_star words it (every N): 4096 mixed meshes held by rank 0 in its HBM -> LPT plan from the
+            walk tapes -> ONE grouped NCCL send/recv into each rank's device arena -> every rank decodes its bin; scatter_ms,
+            decode_ms, LPT max/mean load, strong-scaling value; the gather of one output arena timed separately.
+  secondary (N=1) tarta x 64, configs[4], configs[2] device-resident, and the latency of ONE configs[0] mesh through the
+            crt::Decoder-shaped host call next to the reference's.
 
 Inputs: the synthetic meshes are ENCODED by the reference's own Encoder (oracle/workloads.py -> oracle/_ref; this repo has no
 encoder, SURVEY §8 puts it out of scope) as set-up before anything is timed; without oracle/_ref one pre-encoded blob per
